@@ -1,0 +1,200 @@
+/*
+ * prisma_b200.h -- C ABI of libprisma_b200.so (sm_100a).
+ *
+ * The reference (Prisma-Multimodal/ViT-Prisma) has no FFI: its two hot paths are Python
+ * methods that hand every flop to PyTorch ATen.  This header is the boundary a maintainer
+ * binds instead (ctypes stub in INTEGRATION.md): plain pointers + sizes + a CUDA stream,
+ * no torch types.  Every entry point names the reference code it stands in for
+ * (paths relative to /root/reference/src/vit_prisma).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - matrices are row-major; "ld*" are row strides in ELEMENTS;
+ *   - weights enter GEMMs "K-major": B is [N][K] (one output column's weights contiguous);
+ *   - return 0 on success, a negative PB_E* code otherwise; pb_last_error() gives the text.
+ *     Nothing throws, nothing falls back to a CPU path.
+ *   - launches go to the stream passed in; no internal host threads, no hidden syncs.
+ */
+#ifndef PRISMA_B200_H
+#define PRISMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pb_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define PB_API __attribute__((visibility("default")))
+#else
+#define PB_API
+#endif
+
+enum { PB_OK = 0, PB_EINVAL = -1, PB_ECUDA = -2, PB_EUNSUPPORTED = -3, PB_ENODEVICE = -4 };
+enum { PB_F32 = 0, PB_BF16 = 1 };
+/* activation_name of HookedViTConfig (models/layers/mlp.py:41-62, models/activation_fns.py:19-58) */
+enum { PB_ACT_NONE = 0, PB_ACT_RELU = 1, PB_ACT_GELU = 2, PB_ACT_SILU = 3, PB_ACT_GELU_NEW = 4,
+       PB_ACT_GELU_FAST = 5, PB_ACT_QUICK_GELU = 6, PB_ACT_TANH_RELU = 7, PB_ACT_EXP = 8 };
+enum { PB_GEMM_AUTO = 0, PB_GEMM_SIMT = 1, PB_GEMM_TC = 2 };
+
+/* ---------------------------------------------------------------- library */
+PB_API int pb_version(void);
+PB_API const char* pb_last_error(void);
+/* fills sm count / compute capability of the current device; PB_ENODEVICE without a GPU */
+PB_API int pb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* sizeof() of the ABI structs as compiled (0 PbGemm, 1 PbLayerNorm, 2 PbAttention, 3 PbVitLayerW,
+ * 4 PbVitLayerSpill, 5 PbVitForward, ...; -1 for an unknown index): lets a binding verify its layout */
+PB_API int pb_abi_sizeof(int which);
+
+/* ------------------------------------------------------------------- GEMM
+ * out = A[M,K] @ B[N,K]^T (+bias), fp32 accumulate.  Stands in for every
+ * fancy_einsum/einops.einsum contraction on the two paths:
+ *   models/layers/attention.py:158-244 (Q/K/V/O), mlp.py:69,78, head.py:31,
+ *   patch_embedding.py:14-32 (stride==kernel conv as a GEMM), sae/sae.py:568,585.
+ * Epilogue: out0 = acc + bias                       (the "pre" hook point; NULL = skip)
+ *           out1 = act(out0)  or  residual + out0   (NULL = skip)
+ * With n_split > 1 the N axis is cut into n_split blocks of split_n columns and block j
+ * of out0 goes to out_split[j] (row stride ld0): one launch fills hook_q / hook_k / hook_v.
+ * dtype PB_F32 : impl SIMT  -> exact fp32 FFMA;
+ *                impl TC    -> tcgen05 kind::tf32 in 3 passes (A, A_lo, B, B_lo all required;
+ *                              *_lo = x - tf32_trunc(x), see pb_split_tf32) ~fp32 accuracy.
+ * dtype PB_BF16: impl TC    -> tcgen05 kind::f16 (bf16 in, fp32 accumulate in TMEM).
+ * impl AUTO picks TC when the shape/alignment allows it, else SIMT.                         */
+typedef struct {
+  int32_t M, N, K;
+  int32_t dtype, act, impl;
+  const void* A;  int64_t lda;
+  const void* B;  int64_t ldb;
+  const void* A_lo; const void* B_lo;
+  const void* bias;
+  const void* residual; int64_t ldr;
+  void* out0; int64_t ld0;
+  void* out1; int64_t ld1;
+  float* out1_lo;                    /* F32 only: tf32 residual of out1 (row stride ld1), or NULL */
+  int32_t n_split, split_n;
+  void* out_split[4];
+} PbGemm;
+PB_API int pb_gemm(const PbGemm* g, pb_stream_t stream);
+/* lo[i] = x[i] - float(tf32_trunc(x[i]))  (the residual operand of the 3xTF32 scheme) */
+PB_API int pb_split_tf32(const float* x, float* lo, int64_t n, pb_stream_t stream);
+
+/* -------------------------------------------------------------- LayerNorm
+ * models/layers/layer_norm.py:27-45 (LayerNormPre: w == b == NULL) and :75-93 (LayerNorm):
+ *   xc = x - mean(x);  scale = sqrt(mean(xc^2) + eps);  y = xc/scale * w + b
+ * x is read in dtype_in, arithmetic is fp32 (the reference upcasts non-fp32 inputs).
+ *   scale     fp32 [rows]            -> hook_scale        (NULL = skip)
+ *   norm_f32  fp32 [rows, cols]      -> hook_normalized when dtype_out != F32 (NULL = skip)
+ *   out       dtype_out [rows, cols] -> the tensor downstream code consumes
+ *   out_lo    fp32 [rows, cols]      -> tf32 residual of out for a following 3xTF32 GEMM
+ *   scale_in  fp32 [rows] or NULL    -> when given, divide by THIS scale instead of the computed one
+ *                                       (a user hook replaced / edited hook_scale's value)        */
+typedef struct {
+  int64_t rows; int32_t cols;
+  int32_t dtype_in, dtype_out;
+  float eps;
+  const void* x; const void* w; const void* b;
+  float* scale; float* norm_f32; void* out; float* out_lo;
+  const float* scale_in;
+} PbLayerNorm;
+PB_API int pb_layernorm(const PbLayerNorm* p, pb_stream_t stream);
+
+/* -------------------------------------------------------------- Attention
+ * models/layers/attention.py:126-184, 246-281.  q,k,v,z: [B,T,H,dh]; scores,pattern: [B,H,T,T].
+ *   scores  = q k^T / attn_scale          (hook_attn_scores; NULL = not materialised)
+ *   pattern = softmax(scores), NaN -> 0   (hook_pattern;     NULL = not materialised)
+ *   z       = pattern v                   (hook_z)
+ * pb_attention runs all three in one kernel; the three split entry points exist for the
+ * hooked path where user code may edit scores / pattern between the steps.               */
+typedef struct {
+  int32_t B, T, H, dh, dtype;
+  float attn_scale;
+  const void* q; const void* k; const void* v;
+  void* scores; void* pattern; void* z;
+} PbAttention;
+PB_API int pb_attention(const PbAttention* p, pb_stream_t stream);
+PB_API int pb_attn_scores(const PbAttention* p, pb_stream_t stream);              /* q,k -> scores   */
+PB_API int pb_softmax_rows(const void* x, void* y, int64_t rows, int32_t cols, int32_t dtype,
+                    pb_stream_t stream);                                   /* softmax, NaN->0 */
+PB_API int pb_attn_pv(const PbAttention* p, pb_stream_t stream);                  /* pattern,v -> z  */
+
+/* ------------------------------------------------------------ element-wise */
+PB_API int pb_add(const void* a, const void* b, void* out, int64_t n, int32_t dtype, pb_stream_t s);
+PB_API int pb_mul(const void* a, const void* b, void* out, int64_t n, int32_t dtype, pb_stream_t s);
+PB_API int pb_activation(const void* x, void* y, int64_t n, int32_t act, int32_t dtype, pb_stream_t s);
+/* out[r,:] = x[r,:] / max(||x[r,:]||_2, eps)     (F.normalize, models/base_vit.py:214-215) */
+PB_API int pb_l2_normalize_rows(const void* x, void* out, int64_t rows, int32_t cols, float eps,
+                         int32_t dtype, pb_stream_t s);
+/* out[b,:] = mean_t x[b,t,:]                      (classification_type "gaap", base_vit.py:195-198) */
+PB_API int pb_mean_tokens(const void* x, void* out, int32_t B, int32_t T, int32_t d, int32_t dtype,
+                   pb_stream_t s);
+/* images [B,C,S,S] -> patches [B*(S/P)^2, C*P*P] in conv-weight order (patch_embedding.py:26-32) */
+PB_API int pb_im2col_patches(const void* images, void* patches, int32_t B, int32_t C, int32_t S,
+                      int32_t P, int32_t dtype, pb_stream_t s);
+/* full[b,0,:] = cls + pos[0];  full[b,1+i,:] = embed[b,i,:] + pos[1+i]  (base_vit.py:171-179)
+ * with use_cls == 0: full[b,i,:] = embed[b,i,:] + pos[i]                                  */
+PB_API int pb_embed_assemble(const void* embed, const void* cls, const void* pos, void* full,
+                      int32_t B, int32_t n_patches, int32_t d, int32_t use_cls, int32_t dtype,
+                      pb_stream_t s);
+PB_API int pb_cast(const void* x, int32_t dtype_in, void* y, int32_t dtype_out, int64_t n, pb_stream_t s);
+
+/* ------------------------------------------------ fused HookedViT forward
+ * One call = HookedViT.forward (models/base_vit.py:152-217) with every requested HookPoint
+ * activation spilled to its destination (prisma_tools/hooked_root_module.py:289-332 _save_hook).
+ * Weight pointers are the K-major packs built by the host (vit_prisma/b200/vit_engine.py):
+ *   wqkv [3*H*dh][d]  rows: q heads, k heads, v heads  <- W_Q/W_K/W_V [H,d,dh]
+ *   wo   [d][H*dh]                                     <- W_O [H,dh,d]
+ *   win  [d_mlp][d], wout [d][d_mlp]                   <- W_in [d,d_mlp], W_out [d_mlp,d]
+ * A NULL spill pointer means "hook point not requested": the tensor is then never written to
+ * HBM unless a later kernel needs it, in which case the host passes a scratch pointer.      */
+typedef struct {
+  const void *ln1_w, *ln1_b, *wqkv, *wqkv_lo, *bqkv, *wo, *wo_lo, *bo;
+  const void *ln2_w, *ln2_b, *win, *win_lo, *bin, *wout, *wout_lo, *bout;
+} PbVitLayerW;
+
+typedef struct {
+  float* ln1_scale;  float* ln1_norm_f32;  void* ln1_out;
+  void *q, *k, *v;
+  void *scores, *pattern;
+  void* z;
+  void* attn_out;    void* resid_mid;
+  float* ln2_scale;  float* ln2_norm_f32;  void* ln2_out;
+  void* pre;         void* post;
+  void* mlp_out;     void* resid_post;
+} PbVitLayerSpill;
+
+typedef struct {
+  /* geometry */
+  int32_t batch, n_channels, image_size, patch_size, n_patches, n_tokens;
+  int32_t d_model, n_heads, d_head, d_mlp, n_classes;
+  int32_t n_layers_run;      /* blocks executed (stop_at_layer) */
+  int32_t run_head;          /* 0: return residual after the last executed block */
+  int32_t use_cls, layer_norm_pre, normalize_output, head_proj /* return_type != pre_logits */;
+  int32_t pool_gaap;         /* classification_type: 0 = cls token (row 0), 1 = mean over tokens */
+  int32_t act, dtype, gemm_impl;
+  float eps, attn_scale;
+  /* inputs + weights */
+  const void* images;
+  const void *patch_w, *patch_w_lo, *patch_b, *cls, *pos;
+  const void *lnpre_w, *lnpre_b, *lnf_w, *lnf_b, *head_w, *head_w_lo, *head_b;
+  const PbVitLayerW* layers_host;        /* HOST array [n_layers_run] */
+  /* spill destinations / work buffers */
+  void* patches;             /* [B*n_patches, C*P*P] im2col scratch                         */
+  void* embed;               /* hook_embed [B,n_patches,d]                                  */
+  void* full_embed;          /* hook_full_embed == residual before ln_pre [B,T,d]           */
+  float* lnpre_scale; float* lnpre_norm_f32; void* lnpre_out;    /* residual fed to block 0 */
+  const PbVitLayerSpill* spills_host;    /* HOST array [n_layers_run] */
+  float* lnf_scale; float* lnf_norm_f32; void* lnf_out;
+  void* pooled;              /* [B,d] cls/gaap-pooled ln_final output                       */
+  void* pre_normalize;       /* hook_post_head_pre_normalize [B, n_classes or d]            */
+  void* out;                 /* model output                                                */
+  float* lo_scratch;         /* fp32 [max(B*T*(d + max(d_mlp, H*dh)), B*n_patches*C*P*P)]: tf32 residuals of the
+                                GEMM A operands in 3xTF32 mode, or NULL (then fp32 GEMMs run on the exact FFMA path) */
+} PbVitForward;
+PB_API int pb_vit_forward(const PbVitForward* f, pb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRISMA_B200_H */

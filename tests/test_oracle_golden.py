@@ -1,0 +1,57 @@
+"""Pin the oracle (oracle/vit_oracle.py) to fixtures produced by the unmodified reference.
+
+CPU-only: this is the "is the checker right" gate; the CUDA path is then checked against the oracle
+and the same fixtures in test_vit_gpu.py."""
+import pytest
+import torch
+
+from oracle.vit_oracle import CLIP_B32, digest, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
+from tests.util import assert_close, load_golden
+
+TOL = {"fp32": 2e-5, "bf16": 1.6e-2}
+
+
+def _images(batch, cfg, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, cfg["n_channels"], cfg["image_size"], cfg["image_size"], generator=g)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("dname", ["fp32", "bf16"])
+def test_oracle_matches_reference_tiny(tag, dname):
+    gold = load_golden(f"vit_tiny_{tag}_{dname}.pt")
+    cfg = dict(gold["cfg"])
+    dtype = torch.float32 if dname == "fp32" else torch.bfloat16
+    cfg["dtype"] = dtype
+    assert state_dict_shapes(cfg) == gold["shapes"], "state-dict layout drifted from the reference"
+    sd = recipe_state_dict(gold["shapes"], gold["weights_seed"], dtype)
+    x = _images(gold["batch"], cfg, gold["images_seed"]).to(dtype)
+    out, cache = vit_forward_with_cache(sd, cfg, x)
+    assert list(cache.keys()) == gold["keys"], "cache key order differs from the reference"
+    for k in gold["keys"]:
+        assert_close(cache[k], gold["cache"][k], TOL[dname], k)
+    assert_close(out, gold["out"], TOL[dname], "model output")
+    # names_filter + stop_at_layer exactly as VisionActivationsStore.get_activations uses them
+    flt = ["blocks.0.hook_resid_post", "blocks.1.ln1.hook_normalized"]
+    stop_out, stop_cache = vit_forward_with_cache(sd, cfg, x, names_filter=lambda n: n in flt, stop_at_layer=1)
+    assert list(stop_cache.keys()) == gold["stop_keys"]
+    assert_close(stop_out, gold["stop_out"], TOL[dname], "stop_at_layer output")
+
+
+def test_oracle_matches_reference_clip_b32_digest():
+    gold = load_golden("vit_b32_fp32_digest.pt")
+    cfg = dict(gold["cfg"])
+    assert cfg == CLIP_B32
+    sd = recipe_state_dict(state_dict_shapes(cfg), gold["weights_seed"])
+    x = _images(gold["batch"], cfg, gold["images_seed"])
+    out, cache = vit_forward_with_cache(sd, cfg, x)
+    assert list(cache.keys()) == gold["keys"]
+    assert len(cache) == 214
+    assert sum(v.numel() * v.element_size() for v in cache.values()) == gold["bytes_materialised"] == 4 * 38_980_176
+    for k, dg in gold["digests"].items():
+        mine = digest(cache[k])
+        assert mine["shape"] == dg["shape"] and mine["dtype"] == dg["dtype"], k
+        scale = max(dg["max_abs"], 1e-30)
+        assert (mine["samples"] - dg["samples"]).abs().max().item() / scale < 2e-5, k
+        assert abs(mine["sum"] - dg["sum"]) <= 2e-5 * max(dg["abs_sum"], 1e-30), k
+    assert_close(out, gold["out"], 2e-5, "model output")

@@ -1,0 +1,331 @@
+// gemm_tc.cu -- tcgen05 / TMEM / TMA GEMM with the hooked epilogue (sm_100a).
+//
+//   out = A[M,K] @ B[N,K]^T, both operands K-major in HBM, fp32 accumulation in tensor memory.
+//
+// One CTA computes one 128 x BN output tile:
+//   warp 0   TMA producer : cp.async.bulk.tensor.2d (128B-swizzled boxes, one k-slab of 128 bytes per row)
+//                           into a STAGES-deep shared-memory ring, completion on "full" mbarriers;
+//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma (M=128, N=BN, K=32 bytes per instruction)
+//                           straight from the swizzled tiles through shared-memory descriptors;
+//                           tcgen05.commit releases ring slots ("empty") and finally signals "accumulator ready";
+//   warps 2-5 epilogue    : tcgen05.ld (32 lanes x 32 columns per instruction) TMEM -> registers,
+//                           bias / activation / residual, hook-point spill to up to two destinations.
+// Two CTAs fit per SM in the bf16 configuration (3 x 32 KB ring + 128 TMEM columns each), so one CTA's
+// epilogue (the HBM-store-heavy part of a hooked GEMM) overlaps the other's mainloop.
+//
+// Precision modes
+//   bf16  : kind::f16, bf16 operands.                       1 MMA per k-step
+//   tf32x3: kind::tf32 on fp32 operands split as x = hi + lo with hi = tf32_trunc(x) (the tensor core
+//           ignores the 13 low mantissa bits, so the unsplit fp32 array *is* hi) and lo = x - hi stored
+//           separately:  A@B ~= Alo@Bhi + Ahi@Blo + Ahi@Bhi (lo*lo ~ 2^-22 relative is dropped).
+//           3 MMAs per k-step into the same accumulator -> fp32-grade products for the 1e-4 parity bar.
+#include "common.cuh"
+#include "gemm_epi.cuh"
+#include <cuda.h>
+
+namespace {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug turns into a trap (-> CUDA error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("gemm_tc: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int KIND>  // 0: kind::f16 (bf16 in), 1: kind::tf32
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+//   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4   = 1024 B between 8-row groups (rows are 128 B, stored densely by TMA)
+//   [46,48) descriptor version = 1 (sm_100)      [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 192;
+
+template <typename T, int NPASS, int BN, int STAGES>
+struct TcCfg {
+  static constexpr int ES = sizeof(T);
+  static constexpr int BK = 128 / ES;       // elements per 128-byte k-slab
+  static constexpr int UMMA_K_BYTES = 32;   // one tcgen05.mma consumes 32 bytes of K per row
+  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int NOP = NPASS == 3 ? 2 : 1;  // operand copies per matrix (hi [+ lo])
+  static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers + tmem ptr*/;
+  static constexpr uint32_t FMT = sizeof(T) == 2 ? 1u : 2u;  // F16F32Format: BF16 = 1, TF32 = 2
+  // cute::UMMA::InstrDescriptor: c_format F32 [4,6) | a_format [7,10) | b_format [10,13) | a/b K-major (0) | N>>3 [17,23) | M>>4 [24,29)
+  static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+};
+
+template <typename T, int NPASS, int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                        const __grid_constant__ CUtensorMap tmAlo,
+                                                        const __grid_constant__ CUtensorMap tmBlo, int K, EpiParams ep) {
+  using C = TcCfg<T, NPASS, BN, STAGES>;
+  constexpr int KIND = sizeof(T) == 2 ? 0 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t bar_base = ring + C::RING_BYTES;
+  // barrier block: full[STAGES] | empty[STAGES] | tmem_full | tmem_ptr(u32)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int num_kb = (K + C::BK - 1) / C::BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (NPASS == 3) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: one warp, BN fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+        const uint32_t sa = ring + s * C::STAGE_BYTES;
+        const int kc = kb * C::BK;
+        tma_load_2d(sa, &tmA, full_bar(s), kc, m0);
+        if (NPASS == 3) tma_load_2d(sa + C::A_BYTES, &tmAlo, full_bar(s), kc, m0);
+        const uint32_t sb = sa + C::NOP * C::A_BYTES;
+        tma_load_2d(sb, &tmB, full_bar(s), kc, n0);
+        if (NPASS == 3) tma_load_2d(sb + C::B_BYTES, &tmBlo, full_bar(s), kc, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = ring + s * C::STAGE_BYTES;
+        const uint32_t sb = sa + C::NOP * C::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 128 / C::UMMA_K_BYTES; ++k) {
+          const uint32_t koff = k * C::UMMA_K_BYTES;
+          const uint64_t a_hi = make_smem_desc(sa + koff);
+          const uint64_t b_hi = make_smem_desc(sb + koff);
+          const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+          if (NPASS == 3) {
+            const uint64_t a_lo = make_smem_desc(sa + C::A_BYTES + koff);
+            const uint64_t b_lo = make_smem_desc(sb + C::B_BYTES + koff);
+            tc_mma<KIND>(tmem_base, a_lo, b_hi, C::IDESC, first);
+            tc_mma<KIND>(tmem_base, a_hi, b_lo, C::IDESC, 1u);
+            tc_mma<KIND>(tmem_base, a_hi, b_hi, C::IDESC, 1u);
+          } else {
+            tc_mma<KIND>(tmem_base, a_hi, b_hi, C::IDESC, first);
+          }
+        }
+        tc_commit(empty_bar(s));  // slot reusable once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + quarter * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      if (row < ep.M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = n0 + c * 32 + j * 4;
+          if (col < ep.N) {
+            float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
+            epilogue_store4<T>(ep, row, col, v);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D map over a row-major [rows, cols] matrix with row stride ld (elements); box = [box_rows, 128 bytes]
+int make_map(CUtensorMap* map, const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { pb_set_error("gemm_tc: cuTensorMapEncodeTiled entry point unavailable"); return PB_ECUDA; }
+  const int es = dtype == PB_BF16 ? 2 : 4;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, dtype == PB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim,
+                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    pb_set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)rc, (long long)rows, (long long)cols, (long long)ld);
+    return PB_ECUDA;
+  }
+  return PB_OK;
+}
+
+template <typename T, int NPASS, int BN, int STAGES>
+int launch_tc(const PbGemm* g, cudaStream_t st) {
+  using C = TcCfg<T, NPASS, BN, STAGES>;
+  CUtensorMap tmA, tmB, tmAlo, tmBlo;
+  PB_TRY(make_map(&tmA, g->A, g->dtype, g->M, g->K, g->lda, TC_BM));
+  PB_TRY(make_map(&tmB, g->B, g->dtype, g->N, g->K, g->ldb, BN));
+  if (NPASS == 3) {
+    PB_TRY(make_map(&tmAlo, g->A_lo, g->dtype, g->M, g->K, g->lda, TC_BM));
+    PB_TRY(make_map(&tmBlo, g->B_lo, g->dtype, g->N, g->K, g->ldb, BN));
+  } else {
+    tmAlo = tmA;
+    tmBlo = tmB;
+  }
+  auto kern = k_gemm_tc<T, NPASS, BN, STAGES>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  EpiParams ep = pb_make_epi(g);
+  dim3 grid((g->N + BN - 1) / BN, (g->M + TC_BM - 1) / TC_BM);
+  kern<<<grid, TC_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, tmAlo, tmBlo, g->K, ep);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+}  // namespace
+
+// shape / alignment gate for the tensor-core path
+bool pb_gemm_tc_eligible(const PbGemm* g) {
+  const int es = g->dtype == PB_BF16 ? 2 : 4;
+  if (g->M < 1 || g->N < 16 || g->K < 128 / es) return false;
+  if (!pb_aligned16(g->A) || !pb_aligned16(g->B)) return false;
+  if ((g->lda * es) % 16 != 0 || (g->ldb * es) % 16 != 0) return false;
+  if (g->dtype == PB_F32) {
+    if (!g->A_lo || !g->B_lo) return false;
+    if (!pb_aligned16(g->A_lo) || !pb_aligned16(g->B_lo)) return false;
+  }
+  return true;
+}
+
+int pb_gemm_tc(const PbGemm* g, cudaStream_t st) {
+  if (!pb_gemm_tc_eligible(g)) {
+    pb_set_error("pb_gemm: tensor-core path refused M=%d N=%d K=%d dtype=%d lda=%lld ldb=%lld (alignment / missing *_lo)", g->M, g->N, g->K,
+                 g->dtype, (long long)g->lda, (long long)g->ldb);
+    return PB_EUNSUPPORTED;
+  }
+  if (g->dtype == PB_BF16) return launch_tc<bf16, 1, 128, 3>(g, st);
+  return launch_tc<float, 3, 128, 3>(g, st);
+}
