@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on a B200: HookedViT.run_with_cache images/sec (+ SAE tokens/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload vit|sae]
+                    [--dtype fp32|bf16] [--batch B]
+
+Prints ONE JSON line (contract in the task statement):
+  value      whole-job throughput with inputs resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e        same metric through the public API with HOST (pinned) inputs: H2D of the batch + the call + D2H
+             of the model output inside the timed region
+  roofline   dominant kernel (MLP-in GEMM with its dual hook-point epilogue), algorithmic flops / CUDA-event time
+             against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (oracle/vit_oracle.py) timed on this box's host cores on a bounded sample
+--impl reference times the CPU implementation (oracle port; /root/reference does not exist on the GPU box).
+A "step" = one run_with_cache over one synthetic batch (cfg #2: CLIP ViT-B/32 geometry, batch 512, all 214 hook points).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "vit-prisma_b200"))
+
+import torch  # noqa: E402
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def _cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------ CPU (oracle port) arm
+def cpu_vit_images_per_sec(budget_s=12.0, batch=16, threads=None):
+    from oracle.vit_oracle import CLIP_B32, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
+    threads = threads or _cpu_cores()
+    torch.set_num_threads(threads)
+    cfg = dict(CLIP_B32)
+    sd = recipe_state_dict(state_dict_shapes(cfg), 1234)
+    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        vit_forward_with_cache(sd, cfg, x)  # warm-up
+        n, t0 = 0, time.perf_counter()
+        while True:
+            vit_forward_with_cache(sd, cfg, x)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt >= budget_s or n >= 64:
+                break
+    return {"value": n * batch / dt, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{n} x run_with_cache(batch {batch}) CLIP ViT-B/32 fp32, all 214 hook points, oracle/vit_oracle.py, {dt:.1f}s"}
+
+
+def run_reference_arm(args):
+    world, rank, _ = _dist()
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    from oracle.vit_oracle import CLIP_B32, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
+    threads = _cpu_cores()
+    torch.set_num_threads(threads)
+    cfg = dict(CLIP_B32)
+    sd = recipe_state_dict(state_dict_shapes(cfg), 1234)
+    batch = 16  # bounded sample of the batch-512 workload: per-image cost is flat in batch on CPU
+    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        for _ in range(max(1, min(warm, 2))):
+            vit_forward_with_cache(sd, cfg, x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            vit_forward_with_cache(sd, cfg, x)
+        dt = time.perf_counter() - t0
+    v = steps * batch / dt
+    line = {"impl": "reference", "metric": "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)", "value": v,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "vit_b32_run_with_cache_all_hooks", "batch_per_step": batch, "note": "bounded sample of the batch-512 workload on host cores"},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"{steps} steps x batch {batch}, oracle/vit_oracle.py (CPU restatement of the reference path)"},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def build_model(dtype, device):
+    from oracle.vit_oracle import CLIP_B32, recipe_state_dict
+    from vit_prisma.configs.HookedViTConfig import HookedViTConfig
+    from vit_prisma.models.base_vit import HookedViT
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = HookedViT(HookedViTConfig(**CLIP_B32, dtype=dtype))
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(recipe_state_dict(shapes, 1234))
+    return model.to(device, dtype).eval()
+
+
+def vit_flops_per_image(cfg):
+    N = (cfg["image_size"] // cfg["patch_size"]) ** 2
+    T = N + 1
+    d, H, dh, M, L = cfg["d_model"], cfg["n_heads"], cfg["d_head"], cfg["d_mlp"], cfg["n_layers"]
+    CPP = cfg["n_channels"] * cfg["patch_size"] ** 2
+    return 2 * N * CPP * d + L * (6 * T * d * H * dh + 4 * H * T * T * dh + 2 * T * H * dh * d + 4 * T * d * M) + 2 * d * cfg["n_classes"]
+
+
+def time_dominant_gemm(model, batch, dtype, iters=10):
+    """MLP-in GEMM (+bias, GELU, two hook-point outputs) at the step's shape, alone on the stream, CUDA events."""
+    from vit_prisma.b200 import ops
+    cfg = model.cfg
+    M, K, N = batch * cfg.n_tokens, cfg.d_model, cfg.d_mlp
+    mlp = model.blocks[0].mlp
+    win, win_lo = mlp.packed_in()
+    a = torch.randn(M, K, device="cuda", dtype=dtype)
+    a_lo = ops.split_tf32(a) if dtype == torch.float32 else None
+    pre = torch.empty(M, N, device="cuda", dtype=dtype)
+    post = torch.empty(M, N, device="cuda", dtype=dtype)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    def call():
+        ops.gemm(a, win, mlp.b_in, act=cfg.activation_name, a_lo=a_lo, w_lo=win_lo, out0=pre, out1=post)
+    for _ in range(3):
+        call()
+    times = []
+    for _ in range(iters):
+        flush.zero_()                      # evict L2 between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); call(); e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    es = 4 if dtype == torch.float32 else 2
+    return {"ms": ms, "flops": 2.0 * M * N * K, "bytes": float(M * K * es + N * K * es + 2 * M * N * es), "shape": [M, N, K]}
+
+
+def run_ours(args):
+    world, rank, local = _dist()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from oracle.vit_oracle import CLIP_B32
+    from vit_prisma.b200 import _lib as L
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    model = build_model(dtype, dev)
+    B = args.batch
+    g = torch.Generator().manual_seed(rank)
+    host = torch.randn(B, 3, 224, 224, generator=g).to(dtype).pin_memory()
+    x = host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        out, cache = model.run_with_cache(x)
+        del cache
+    barrier()
+    n_keys = 0
+    launches0 = L.get_lib().pb_launch_count()
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out, cache = model.run_with_cache(x)
+            n_keys = len(cache)
+            del cache
+        e1.record()
+        barrier()
+        dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = L.get_lib().pb_launch_count() - launches0
+    route = model.last_route
+
+    # ---- end to end: pinned host batch -> H2D -> run_with_cache -> D2H of the model output, every step
+    out_host = torch.empty((B, CLIP_B32["n_classes"]), dtype=dtype).pin_memory()
+    for _ in range(2):
+        xd = host.to(dev, non_blocking=True)
+        out, cache = model.run_with_cache(xd)
+        out_host.copy_(out, non_blocking=True)
+        del cache
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        xd = host.to(dev, non_blocking=True)
+        out, cache = model.run_with_cache(xd)
+        out_host.copy_(out, non_blocking=True)
+        del cache
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    if rank != 0:
+        return
+    peaks = _peaks()
+    imgs = world * B * args.steps
+    value = imgs / (dev_ms / 1e3)
+    e2e = imgs / (e2e_ms / 1e3)
+    kern = time_dominant_gemm(model, B, dtype)
+    flops_img = vit_flops_per_image(CLIP_B32)
+    # fp32 mode executes 3 tensor-core passes per algorithmic flop; the roofline counts ALGORITHMIC flops
+    achieved = kern["flops"] / (kern["ms"] / 1e3) / 1e12
+    roof = {"bound": "tensor", "kernel": "k_gemm_tc (MLP-in GEMM + bias + GELU, hook_pre/hook_post spill)", "achieved": achieved,
+            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+            "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)", "shape_MNK": kern["shape"], "kernel_ms": kern["ms"],
+            "hbm_gbs_of_kernel": kern["bytes"] / (kern["ms"] / 1e3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
+            "passes": 3 if dtype == torch.float32 else 1,
+            "step_algorithmic_tflops": flops_img * imgs / (dev_ms / 1e3) / 1e12,
+            "step_cache_write_gbs": 38_980_176 * (1 if dtype == torch.float32 else 0.5) * imgs / (dev_ms / 1e3) / 1e9}
+    cpu = cpu_vit_images_per_sec()
+    es = 4 if dtype == torch.float32 else 2
+    line = {"metric": "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "vit_b32_run_with_cache_all_hooks", "model": "CLIP ViT-B/32 geometry, seeded synthetic weights",
+                       "batch_per_gpu": B, "global_batch": B * world, "hook_points_cached": n_keys, "route": route,
+                       "gemm": "tcgen05 3xTF32" if dtype == torch.float32 else "tcgen05 bf16",
+                       "cache_bytes_per_image": int(38_980_176 * es / 4), "l2": "working set (cache arena >> 126 MB) larger than L2",
+                       "parallelism": f"dp{world} (images sharded, no collective)"},
+            "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * host.element_size()),
+                    "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()), "ms_per_step": e2e_ms / args.steps},
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vit", choices=["vit", "sae"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=512)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,8 @@ enum { PB_GEMM_AUTO = 0, PB_GEMM_SIMT = 1, PB_GEMM_TC = 2 };
 /* ---------------------------------------------------------------- library */
 PB_API int pb_version(void);
 PB_API const char* pb_last_error(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; bench.py's gpu_launches) */
+PB_API unsigned long long pb_launch_count(void);
 /* fills sm count / compute capability of the current device; PB_ENODEVICE without a GPU */
 PB_API int pb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* sizeof() of the ABI structs as compiled (0 PbGemm, 1 PbLayerNorm, 2 PbAttention, 3 PbVitLayerW,

@@ -28,8 +28,11 @@ void pb_set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
+extern unsigned long long g_pb_launches;  // kernels launched by this library (pb_launch_count)
+
 #define PB_LAUNCH_CHECK()                                                              \
   do {                                                                                 \
+    ++g_pb_launches;                                                                   \
     cudaError_t e__ = cudaGetLastError();                                              \
     if (e__ != cudaSuccess) {                                                          \
       pb_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \

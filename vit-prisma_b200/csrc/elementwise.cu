@@ -16,6 +16,8 @@ void pb_set_error(const char* fmt, ...) {
 }
 extern "C" const char* pb_last_error(void) { return g_err; }
 extern "C" int pb_version(void) { return 100; }
+unsigned long long g_pb_launches = 0;
+extern "C" unsigned long long pb_launch_count(void) { return g_pb_launches; }
 
 int pb_sm_count() {
   static int cached[64] = {0};

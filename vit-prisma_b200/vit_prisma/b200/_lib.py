@@ -84,11 +84,16 @@ class PbVitForward(C.Structure):
     )
 
 
+# index == argument of pb_abi_sizeof(); the layout test walks this list
+ABI_STRUCTS = [PbGemm, PbLayerNorm, PbAttention, PbVitLayerW, PbVitLayerSpill, PbVitForward]
+
 # name -> (restype, argtypes); also the list the "exports every declared symbol" test walks
 SIGNATURES = {
     "pb_version": (i32, []),
     "pb_last_error": (C.c_char_p, []),
     "pb_device_info": (i32, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pb_abi_sizeof": (i32, [i32]),
+    "pb_launch_count": (C.c_ulonglong, []),
     "pb_gemm": (i32, [C.POINTER(PbGemm), vp]),
     "pb_split_tf32": (i32, [vp, vp, i64, vp]),
     "pb_layernorm": (i32, [C.POINTER(PbLayerNorm), vp]),
