@@ -196,6 +196,58 @@ typedef struct {
 } PbVitForward;
 PB_API int pb_vit_forward(const PbVitForward* f, pb_stream_t stream);
 
+/* ------------------------------------------------------- TopK SAE training step
+ * Stands in for StandardSparseAutoencoder.forward + VisionSAETrainer.train_step
+ * (sae/sae.py:557-645, 144-149, 275-297; sae/train_sae.py:278-411) with activation_fn_str == "topk".
+ * All buffers fp32 unless noted; F = d_sae, d = d_in.  The encoder is stored feature-major:
+ * W_encT [F][d] (the module's W_enc [d,F] parameter is a transposed view of the same memory).
+ * One step = pb_sae_prep -> pb_gemm (hidden_pre = sae_in @ W_encT^T + b_enc) -> pb_sae_topk ->
+ *            pb_sae_decode -> pb_sae_backward -> pb_sae_adam, all on one stream, no host sync.      */
+typedef struct {
+  int32_t rows, d, F, k;
+  int32_t norm_mode;        /* cfg.normalize_activations: 0 none, 1 "layer_norm", 2 "constant_norm_rescale" */
+  int32_t training;         /* 0: decode + loss only */
+  int32_t step;             /* optimizer step count t >= 1 (Adam bias correction) */
+  int32_t renorm_decoder;   /* 1: leave W_dec rows unit-norm after the update (= next step's set_decoder_norm_to_unit_norm) */
+  float lr, beta1, beta2, adam_eps, max_grad_norm /* <= 0: no clipping */;
+  /* inputs / parameters */
+  const float* x;           /* [rows][d] raw activations */
+  float* W_encT; float* W_encT_lo; float* W_dec; float* b_enc; float* b_dec;
+  /* per-step work buffers */
+  float *sae_in, *mu, *sd, *xsum;            /* [rows][d], [rows], [rows], [d] (written by pb_sae_prep) */
+  int32_t* idx; float* val;                  /* [rows][k] TopK support of hidden_pre (written by pb_sae_topk) */
+  float* feat_count;                         /* [F] selections per feature this step (zero it before pb_sae_topk) */
+  float *sae_out, *g, *dval;                 /* [rows][d] (optional), [rows][d], [rows][k] */
+  int32_t *csc_off, *csc_cursor, *csc_entries;  /* [F+1], [F], [rows*k] */
+  float *gW_dec, *gW_encT, *gb_enc, *gb_dec;  /* gradients [F][d], [F][d], [F], [d] */
+  float *gcol, *gbdec2;                      /* [d] scratch */
+  float* fired;                              /* [F] number of tokens with a positive activation of feature f */
+  void* scalars;                             /* 8 floats: loss_sum, gnorm_sq, clip_coef, mse, l0, pos_count, grad_norm, - (zero before the step) */
+  /* optimizer + bookkeeping state */
+  float *m_dec, *v_dec, *m_enc, *v_enc, *m_be, *v_be, *m_bd, *v_bd;
+  float* since_fired; float* act_freq;       /* [F] n_forward_passes_since_fired, act_freq_scores (train_sae.py:356-361); may be NULL */
+} PbSaeStep;
+
+/* sae_in = norm_in(x) - b_dec (+ tf32 residual, row mean / std, column sums of x) -- sae.py:78-87, 557-566 */
+PB_API int pb_sae_prep(const float* x, const float* b_dec, float* sae_in, float* sae_in_lo, float* mu, float* sd,
+                       float* xsum, int32_t rows, int32_t d, int32_t norm_mode, pb_stream_t stream);
+/* torch.topk(hidden_pre, k, dim=-1) (sae.py:803-805): idx int32 / val fp32 [rows][k], sorted by value descending,
+ * ties broken towards the lower index; feat_count[f] += 1 per selection (may be NULL);
+ * scratch >= rows * ceil(F / 24576) * k * 8 bytes when F > 24576, else unused.                     */
+PB_API int pb_sae_topk(const float* hidden_pre, int32_t rows, int32_t F, int32_t k, int32_t* idx, float* val,
+                       float* feat_count, void* scratch, int64_t scratch_bytes, pb_stream_t stream);
+/* dense feature_acts [rows][F] = zeros.scatter_(idx, relu(val)) (sae.py:806-808) -- only for callers that need the dense tensor */
+PB_API int pb_sae_scatter_acts(const int32_t* idx, const float* val, float* dense, int32_t rows, int32_t k, int32_t F,
+                               int32_t relu, pb_stream_t stream);
+/* sparse decode + normalised-MSE partials (+ g = dL/d(decoder output) and d(loss)/d(selected pre-activations) when training) */
+PB_API int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream);
+/* per-feature gradients of W_dec / W_enc / b_enc / b_dec, global grad norm, clip coefficient */
+PB_API int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream);
+/* clip -> remove decoder-parallel gradient -> Adam -> decoder row renorm -> dead-feature counters */
+PB_API int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream);
+/* W[f,:] /= ||W[f,:]|| (set_decoder_norm_to_unit_norm, sae.py:275-277); optional tf32 residual */
+PB_API int pb_unit_norm_rows(float* W, float* W_lo, int32_t F, int32_t d, pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,116 @@
+"""ORACLE (test infrastructure, not product code): CPU restatement of the TopK SAE forward and training step.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this, and only
+as the checker.  Restates, with explicit gradient formulas instead of autograd (so the hand-written CUDA backward is
+checked against an independent derivation that is itself pinned to the reference's autograd):
+
+  StandardSparseAutoencoder.encode/decode/forward      sae/sae.py:557-645
+  run-time input normalisation ("layer_norm")           sae/sae.py:78-90
+  _compute_mse_loss                                     sae/sae.py:144-149
+  TopK activation                                       sae/sae.py:795-808
+  set_decoder_norm_to_unit_norm / remove_gradient_...   sae/sae.py:275-297
+  VisionSAETrainer.train_step ordering, clipping, Adam  sae/train_sae.py:278-411 (torch.optim.Adam defaults)
+  cosineannealingwarmup schedule                        sae/training/get_scheduler.py:42-53, train_sae.py:235
+
+Pinning: tests/test_oracle_golden.py compares against tests/golden/sae_tiny_*.pt, produced by running the
+UNMODIFIED reference modules + torch autograd + torch.optim.Adam in the build container
+(tests/golden/make_golden_sae.py).  The reference has no numeric test of this path, so the
+reference itself, run here, is the anchor.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+
+def normalise_in(x: torch.Tensor, mode: str, eps: float = 1e-5):
+    if mode == "layer_norm":                           # sae.py:78-87
+        mu = x.mean(dim=-1, keepdim=True)
+        xc = x - mu
+        std = xc.std(dim=-1, keepdim=True)             # unbiased
+        return xc / (std + eps), mu, std
+    if mode == "constant_norm_rescale":                # sae.py:60-72
+        coeff = (x.shape[-1] ** 0.5) / x.norm(dim=-1, keepdim=True)
+        return x * coeff, torch.zeros_like(coeff), 1.0 / coeff
+    return x, torch.zeros_like(x[..., :1]), torch.ones_like(x[..., :1])
+
+
+def sae_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, k: int, mode: str = "layer_norm") -> Dict[str, torch.Tensor]:
+    """p: W_enc [d,F], W_dec [F,d], b_enc [F], b_dec [d]."""
+    xn, mu, std = normalise_in(x, mode)
+    sae_in = xn - p["b_dec"]                            # sae.py:564-566
+    hidden_pre = sae_in @ p["W_enc"] + p["b_enc"]      # :568-574
+    top = torch.topk(hidden_pre, k=k, dim=-1)           # :803-805
+    vals = torch.relu(top.values)
+    feature_acts = torch.zeros_like(hidden_pre).scatter_(-1, top.indices, vals)   # :806-808
+    out_n = feature_acts @ p["W_dec"] + p["b_dec"]     # :584-592
+    sae_out = out_n * std + mu if mode == "layer_norm" else (out_n * std if mode == "constant_norm_rescale" else out_n)
+    x_centred = x - x.mean(dim=0, keepdim=True)         # :145
+    nf = torch.norm(x_centred, p=2, dim=-1, keepdim=True)
+    mse = (((sae_out - x) ** 2) / nf).mean()            # :146-148
+    return dict(sae_in=sae_in, hidden_pre=hidden_pre, idx=top.indices, raw_val=top.values, feature_acts=feature_acts,
+                sae_out=sae_out, mse=mse, nf=nf, std=std, mu=mu)
+
+
+def sae_grads(p: Dict[str, torch.Tensor], x: torch.Tensor, fwd: Dict[str, torch.Tensor], mode: str = "layer_norm") -> Dict[str, torch.Tensor]:
+    """Gradients of mse wrt the four parameters, closed form (matches loss.backward() of the reference graph)."""
+    Bt, d = x.shape
+    std = fwd["std"] if mode != "none" else torch.ones_like(fwd["nf"])
+    g = 2.0 * (fwd["sae_out"] - x) * std / (fwd["nf"] * Bt * d)          # dL/d out_n
+    acts = fwd["feature_acts"]
+    gW_dec = acts.t() @ g
+    d_acts = g @ p["W_dec"].t()
+    d_pre = d_acts * (acts > 0)                                           # TopK mask AND ReLU mask
+    gW_enc = fwd["sae_in"].t() @ d_pre
+    gb_enc = d_pre.sum(0)
+    d_sae_in = d_pre @ p["W_enc"].t()
+    gb_dec = g.sum(0) - d_sae_in.sum(0)                                   # decoder bias + (sae_in = xn - b_dec)
+    return dict(W_enc=gW_enc, W_dec=gW_dec, b_enc=gb_enc, b_dec=gb_dec)
+
+
+def lr_multiplier(step: int, warm_up_steps: int, training_steps: int, lr_end: float) -> float:
+    """get_warmup_cosine_lambda (get_scheduler.py:42-53); note lr_end is used as a *multiplier* (train_sae.py:235 passes lr/10)."""
+    if step < warm_up_steps:
+        return (step + 1) / warm_up_steps
+    progress = (step - warm_up_steps) / (training_steps - warm_up_steps)
+    return lr_end + 0.5 * (1 - lr_end) * (1 + math.cos(math.pi * progress))
+
+
+def new_adam_state(p: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, torch.Tensor]]:
+    return {k: dict(m=torch.zeros_like(v), v=torch.zeros_like(v)) for k, v in p.items()}
+
+
+def sae_train_step(p: Dict[str, torch.Tensor], state, x: torch.Tensor, k: int, lr: float, t: int, mode: str = "layer_norm",
+                   max_grad_norm: Optional[float] = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                   since_fired: Optional[torch.Tensor] = None, act_freq: Optional[torch.Tensor] = None):
+    """One reference train_step (train_sae.py:278-411), in place on p / state.  t = 1-based optimizer step."""
+    p["W_dec"] /= torch.norm(p["W_dec"], dim=1, keepdim=True)             # :307 set_decoder_norm_to_unit_norm
+    fwd = sae_forward(p, x, k, mode)
+    grads = sae_grads(p, x, fwd, mode)
+    raw_grads = {n: g.clone() for n, g in grads.items()}
+    acts = fwd["feature_acts"]
+    if since_fired is not None:                                           # :356-361
+        did_fire = (acts > 0).float().sum(-2) > 0
+        since_fired += 1
+        since_fired[did_fire] = 0
+    if act_freq is not None:
+        act_freq += (acts.abs() > 0).float().sum(0)
+    l0 = (acts > 0).float().sum(-1).mean()
+    total_norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+    clip = 1.0
+    if max_grad_norm:                                                     # :394-397 clip_grad_norm_
+        clip = min(1.0, max_grad_norm / (total_norm.item() + 1e-6))
+        for g in grads.values():
+            g *= clip
+    par = (grads["W_dec"] * p["W_dec"]).sum(1, keepdim=True)              # :399 / sae.py:279-297
+    grads["W_dec"] = grads["W_dec"] - par * p["W_dec"]
+    b1, b2 = betas
+    for name in p:                                                        # torch.optim.Adam (no amsgrad, no weight decay)
+        st, g = state[name], grads[name]
+        st["m"].mul_(b1).add_(g, alpha=1 - b1)
+        st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = st["v"].sqrt() / math.sqrt(1 - b2 ** t) + eps
+        p[name] -= (lr / (1 - b1 ** t)) * st["m"] / denom
+    return dict(mse=fwd["mse"], l0=l0, grad_norm=total_norm, clip=clip, idx=fwd["idx"], fwd=fwd, grads=grads, raw_grads=raw_grads)

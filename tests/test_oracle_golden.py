@@ -55,3 +55,43 @@ def test_oracle_matches_reference_clip_b32_digest():
         assert (mine["samples"] - dg["samples"]).abs().max().item() / scale < 2e-5, k
         assert abs(mine["sum"] - dg["sum"]) <= 2e-5 * max(dg["abs_sum"], 1e-30), k
     assert_close(out, gold["out"], 2e-5, "model output")
+
+
+# ------------------------------------------------------------------------------------------ SAE
+from oracle.sae_oracle import lr_multiplier, new_adam_state, sae_forward, sae_train_step  # noqa: E402
+
+
+def _sae_data(gold):
+    g = torch.Generator().manual_seed(gold["data_seed"])
+    n, d = gold["batch"] * gold["n_steps"], gold["d_in"]
+    return torch.randn(n, d, generator=g) * 2.0 + torch.randn(d, generator=g)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_sae_oracle_matches_reference_training(tag):
+    """Forward, TopK support, closed-form gradients, clipping, projection, Adam and the LR schedule of the oracle
+    against torch autograd + torch.optim.Adam driving the reference's own SAE module for 6 steps."""
+    gold = load_golden(f"sae_tiny_{tag}.pt")
+    data = _sae_data(gold)
+    p = {k: v.clone() for k, v in gold["init"].items()}
+    state = new_adam_state(p)
+    since_fired, act_freq = torch.zeros(gold["d_sae"]), torch.zeros(gold["d_sae"])
+    B, k = gold["batch"], gold["k"]
+    for s, rec in enumerate(gold["steps"]):
+        x = data[s * B:(s + 1) * B]
+        lr = gold["lr"] * lr_multiplier(s, gold["warm_up_steps"], gold["total_steps"], gold["lr_end"])
+        assert abs(lr - rec["lr"]) < 1e-12
+        out = sae_train_step(p, state, x, k, lr, s + 1, mode=gold["norm"], since_fired=since_fired, act_freq=act_freq)
+        assert torch.equal(out["idx"], rec["topk_idx"]), f"step {s}: TopK indices differ"
+        assert abs(out["mse"].item() - rec["mse"]) <= 1e-5 * abs(rec["mse"])
+        assert abs(out["grad_norm"].item() - rec["grad_norm"]) <= 1e-4 * rec["grad_norm"]
+        assert abs(out["l0"].item() - rec["l0"]) < 1e-6
+        assert_close(out["fwd"]["sae_out"], rec["sae_out"], 1e-5, f"step {s} sae_out")
+        if "raw_grads" in rec:
+            for n in p:
+                assert_close(out["raw_grads"][n], rec["raw_grads"][n], 2e-5, f"raw grad {n}")
+                assert_close(out["grads"][n], rec["final_grads"][n], 2e-5, f"clipped+projected grad {n}")
+        if "params_after" in rec:
+            for n in p:
+                assert_close(p[n], rec["params_after"][n], 2e-5, f"step {s} param {n}")
+    assert torch.equal(since_fired, gold["since_fired"]) and torch.equal(act_freq, gold["act_freq"])

@@ -1,3 +1,815 @@
-// sae.cu -- sparse-autoencoder training path (placeholder until the kernels land in this file).
+// sae.cu -- TopK sparse-autoencoder forward / training step (reference sae/sae.py:32-645,
+// sae/train_sae.py:278-411) as HBM-bound sm_100a kernels around one tensor-core GEMM.
+//
+// Data layout in HBM (all fp32, F = d_sae, d = d_in, Bt = tokens per step):
+//   W_encT [F][d]   encoder, stored feature-major (the nn.Parameter W_enc [d,F] is a transposed VIEW of it):
+//                   K-major B operand of the encoder GEMM, and one contiguous row per feature for the optimizer
+//   W_dec  [F][d]   decoder rows (unit norm on entry to every step)
+//   idx/val [Bt][k] TopK support of hidden_pre per token (sorted by value, descending) -- the only "feature_acts"
+//                   the training step ever materialises; the dense [Bt][F] form exists only on request
+//   csc_*           the same support transposed (per feature: the tokens that selected it) for the weight gradients
+//
+// Step = prep -> encoder GEMM (gemm_tc.cu, 3xTF32) -> topk -> decode+loss+d_hidden -> csc build ->
+//        per-feature gradients (+global grad-norm partials) -> finalize (clip coefficient) ->
+//        fused clip + decoder-parallel-gradient removal + Adam + decoder row renorm + dead-feature counters.
+// No host synchronisation anywhere: scalars (loss, norm, clip coefficient) live in a device struct.
 #include "common.cuh"
-int pb_abi_sizeof_sae(int which) { (void)which; return -1; }
+
+// ---------------------------------------------------------------------------------------------
+// device scalars of one step
+struct SaeScalars {
+  float loss_sum;      // sum_b sum_c (out-x)^2 / nf[b]            (mse = loss_sum / (Bt*d))
+  float gnorm_sq;      // sum of squares of all gradient entries (pre-clip)
+  float clip_coef;     // min(1, max_norm / (norm + 1e-6))
+  float mse;           // loss_sum / (Bt*d)
+  float l0;            // mean number of positive activations per token
+  float pos_count;     // accumulator for l0
+  float grad_norm;     // sqrt(gnorm_sq)
+  float reserved;
+};
+
+// ---------------------------------------------------------------------------------------------
+// 1. prep: run-time input normalisation + decoder-bias subtraction (sae.py:78-87, 557-566)
+//    layer_norm mode: mu = mean(x); xc = x - mu; std = unbiased std(xc); xn = xc / (std + 1e-5)
+//    sae_in = xn - b_dec ;  sae_in_lo = tf32 residual (A operand of the 3xTF32 encoder GEMM)
+//    xsum[c] += x[b,c]  (batch mean for _compute_mse_loss's centring, sae.py:145)
+// one warp per token row; row kept in registers.
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) k_sae_prep(const float* __restrict__ x, const float* __restrict__ b_dec, float* __restrict__ sae_in,
+                                                  float* __restrict__ sae_in_lo, float* __restrict__ mu_out, float* __restrict__ std_out,
+                                                  int rows, int d, int norm_mode, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = d >> 2;
+  const float* xr = x + (int64_t)row * d;
+  float v[CHUNKS][4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c4 = i * 32 + lane;
+    if (c4 < nvec) { ld4(xr + 4 * c4, v[i]); sum += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]); }
+    else v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+  }
+  float mu = 0.f, inv = 1.f, sd = 1.f;
+  if (norm_mode == 1) {  // layer_norm
+    mu = warp_sum(sum) / (float)d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[i][j] -= mu; sq += v[i][j] * v[i][j]; }
+      }
+    }
+    sd = sqrtf(warp_sum(sq) / (float)(d - 1));   // torch.std: Bessel-corrected
+    inv = 1.f / (sd + eps);
+  } else if (norm_mode == 2) {  // constant_norm_rescale: x * sqrt(d) / ||x||
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sq += v[i][j] * v[i][j];
+    sd = sqrtf(warp_sum(sq)) / sqrtf((float)d);   // x_out = x_norm * sd
+    inv = 1.f / sd;
+  }
+  if (lane == 0) {
+    if (mu_out) mu_out[row] = mu;
+    if (std_out) std_out[row] = sd;
+  }
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c4 = i * 32 + lane;
+    if (c4 < nvec) {
+      float bd[4], o[4], lo[4];
+      ld4(b_dec + 4 * c4, bd);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = (norm_mode == 1 ? v[i][j] / (sd + eps) : v[i][j] * inv) - bd[j];
+        lo[j] = o[j] - tf32_trunc(o[j]);
+      }
+      (void)inv;
+      st4(sae_in + (int64_t)row * d + 4 * c4, o);
+      if (sae_in_lo) st4(sae_in_lo + (int64_t)row * d + 4 * c4, lo);
+    }
+  }
+}
+
+// column sums: out[c] += sum_r x[r,c]   (rows split across CTAs, one atomic per column per CTA)
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ x, float* __restrict__ out, int rows, int d, int rows_per_cta) {
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) acc += x[(int64_t)r * d + c];
+    atomicAdd(out + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. top-k per row (sae.py:795-808 torch.topk(x, k, dim=-1), values sorted descending)
+// Exact selection without sorting the row:
+//   (a) each of 256 threads scans its strided share of the row and keeps its best key;
+//   (b) tau = k-th best of the 256 thread-bests: at least k row elements are >= tau, so every true
+//       top-k element is >= tau (keys = (value, lower index wins) are totally ordered -> no tie trouble);
+//   (c) elements >= tau are gathered (typically ~k, at most IPT*k) and ranked by counting;
+//       rank < k writes slot `rank`, which also leaves the output sorted.
+// Rows longer than 256*IPT are cut into segments (grid.y); a second launch merges the per-segment winners.
+__device__ __forceinline__ bool key_gt(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+
+template <int IPT>
+__global__ void __launch_bounds__(256) k_topk(const float* __restrict__ vals, const int* __restrict__ idx_map, int64_t row_stride, int F,
+                                              int seg_len, int k, int* __restrict__ out_idx, float* __restrict__ out_val,
+                                              int64_t out_row_stride, float* __restrict__ feat_count, int cand_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* best_v = reinterpret_cast<float*>(smem_raw);       // [256]
+  int* best_i = reinterpret_cast<int*>(best_v + 256);        // [256]
+  float* cand_v = reinterpret_cast<float*>(best_i + 256);    // [cand_cap]
+  int* cand_i = reinterpret_cast<int*>(cand_v + cand_cap);   // [cand_cap]
+  __shared__ float tau_v;
+  __shared__ int tau_i, cand_n;
+  const int t = threadIdx.x;
+  const int row = blockIdx.x, seg = blockIdx.y;
+  const int s0 = seg * seg_len, s1 = min(F, s0 + seg_len);
+  const float* vr = vals + (int64_t)row * row_stride;
+  const int* mr = idx_map ? idx_map + (int64_t)row * row_stride : nullptr;
+
+  float v[IPT];
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const int p = s0 + t + 256 * i;
+    v[i] = p < s1 ? vr[p] : -INFINITY;
+    const int gi = p < s1 ? (mr ? mr[p] : p) : 0x7fffffff;
+    if (key_gt(v[i], gi, bv, bi)) { bv = v[i]; bi = gi; }
+  }
+  best_v[t] = bv;
+  best_i[t] = bi;
+  if (t == 0) cand_n = 0;
+  __syncthreads();
+  {
+    int rank = 0;
+    for (int j = 0; j < 256; ++j) rank += key_gt(best_v[j], best_i[j], bv, bi) ? 1 : 0;
+    const int kk = min(k, 256);
+    if (rank == kk - 1) { tau_v = bv; tau_i = bi; }
+  }
+  __syncthreads();
+  const float tv = tau_v;
+  const int ti = tau_i;
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const int p = s0 + t + 256 * i;
+    if (p < s1) {
+      const int gi = mr ? mr[p] : p;
+      if (!key_gt(tv, ti, v[i], gi)) {  // key >= tau
+        const int slot = atomicAdd(&cand_n, 1);
+        if (slot < cand_cap) { cand_v[slot] = v[i]; cand_i[slot] = gi; }
+      }
+    }
+  }
+  __syncthreads();
+  const int C = min(cand_n, cand_cap);
+  for (int c = t; c < C; c += 256) {
+    const float cv = cand_v[c];
+    const int ci = cand_i[c];
+    int rank = 0;
+    for (int j = 0; j < C; ++j) rank += key_gt(cand_v[j], cand_i[j], cv, ci) ? 1 : 0;
+    if (rank < k) {
+      const int64_t o = (int64_t)row * out_row_stride + (int64_t)seg * k + rank;
+      out_idx[o] = ci;
+      out_val[o] = cv;
+      if (feat_count) atomicAdd(feat_count + ci, 1.0f);
+    }
+  }
+  // segments shorter than k (only possible for a ragged last segment): pad so the merge pass ignores them
+  if (C < k) {
+    for (int r = C + t; r < k; r += 256) {
+      const int64_t o = (int64_t)row * out_row_stride + (int64_t)seg * k + r;
+      out_idx[o] = 0x7fffffff;
+      out_val[o] = -INFINITY;
+    }
+  }
+}
+
+// dense feature_acts [rows][F] = scatter(relu(val)) -- only when a caller wants the dense tensor (API / hooks)
+__global__ void __launch_bounds__(256) k_scatter_acts(const int* __restrict__ idx, const float* __restrict__ val, float* __restrict__ dense,
+                                                      int rows, int k, int F, int relu) {
+  const int64_t n = (int64_t)rows * k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / k);
+    float v = val[e];
+    if (relu) v = fmaxf(v, 0.f);
+    dense[(int64_t)r * F + idx[e]] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. sparse decode + loss + gradient wrt the selected pre-activations (one warp per token)
+//    out_n  = sum_j relu(val_j) W_dec[idx_j] + b_dec           (sae.py:583-592)
+//    out    = out_n * std + mu                                 (run_time_activation_ln_out, :89-90)
+//    nf     = || x - mean_batch(x) ||_2                        (:145-147)
+//    mse   += sum_c (out - x)^2 / nf ;  g = dL/d out_n = 2 (out - x) std / (nf Bt d)   (:148, mean over all elements)
+//    dval_j = (val_j > 0) * <g, W_dec[idx_j]>                  (backward of decode + ReLU on the TopK support)
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) k_sae_decode(const float* __restrict__ x, const float* __restrict__ xsum, const float* __restrict__ mu,
+                                                    const float* __restrict__ sd, const int* __restrict__ idx, const float* __restrict__ val,
+                                                    const float* __restrict__ W_dec, const float* __restrict__ b_dec,
+                                                    float* __restrict__ sae_out, float* __restrict__ g_out, float* __restrict__ dval,
+                                                    SaeScalars* __restrict__ sc, int rows, int d, int k, int norm_mode, int training,
+                                                    float inv_rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool active = row < rows;
+  const int nvec = d >> 2;
+  float loss_part = 0.f, pos_part = 0.f;
+  if (active) {
+    const int* ir = idx + (int64_t)row * k;
+    const float* vr = val + (int64_t)row * k;
+    float acc[CHUNKS][4];
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) ld4(b_dec + 4 * c4, acc[i]);
+      else acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    }
+    for (int j = 0; j < k; ++j) {
+      const float a = fmaxf(vr[j], 0.f);
+      if (a > 0.f) {
+        pos_part += 1.f;
+        const float* wr = W_dec + (int64_t)ir[j] * d;
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+          const int c4 = i * 32 + lane;
+          if (c4 < nvec) {
+            float w[4];
+            ld4(wr + 4 * c4, w);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][q] = fmaf(a, w[q], acc[i][q]);
+          }
+        }
+      }
+    }
+    const float m = norm_mode ? mu[row] : 0.f;
+    const float s = norm_mode ? sd[row] : 1.f;
+    // pass A: out, centred norm
+    float nsq = 0.f;
+    float e[CHUNKS][4];
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        float xv[4], xs[4], o[4];
+        ld4(x + (int64_t)row * d + 4 * c4, xv);
+        ld4(xsum + 4 * c4, xs);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          o[q] = norm_mode == 1 ? acc[i][q] * s + m : (norm_mode == 2 ? acc[i][q] * s : acc[i][q]);
+          const float xc = xv[q] - xs[q] * inv_rows;
+          nsq += xc * xc;
+          e[i][q] = o[q] - xv[q];
+        }
+        if (sae_out) st4(sae_out + (int64_t)row * d + 4 * c4, o);
+      } else {
+        e[i][0] = e[i][1] = e[i][2] = e[i][3] = 0.f;
+      }
+    }
+    const float nf = sqrtf(warp_sum(nsq));
+    float esq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) esq += e[i][q] * e[i][q];
+    loss_part = warp_sum(esq) / nf;
+    if (training) {
+      // g = dL/d out_n ;  L = sum (out - x)^2 / nf / (rows*d)
+      const float gs = 2.f * s * inv_rows / ((float)d * nf);
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c4 = i * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e[i][q] *= gs;
+        if (c4 < nvec) st4(g_out + (int64_t)row * d + 4 * c4, e[i]);
+      }
+      for (int j = 0; j < k; ++j) {
+        float dot = 0.f;
+        if (vr[j] > 0.f) {
+          const float* wr = W_dec + (int64_t)ir[j] * d;
+#pragma unroll
+          for (int i = 0; i < CHUNKS; ++i) {
+            const int c4 = i * 32 + lane;
+            if (c4 < nvec) {
+              float w[4];
+              ld4(wr + 4 * c4, w);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dot = fmaf(e[i][q], w[q], dot);
+            }
+          }
+          dot = warp_sum(dot);
+        }
+        if (lane == 0) dval[(int64_t)row * k + j] = dot;
+      }
+    }
+  }
+  // one atomic pair per CTA
+  __shared__ float red[2][8];
+  const int w = threadIdx.x >> 5;
+  if (lane == 0) { red[0][w] = active ? loss_part : 0.f; red[1][w] = active ? pos_part : 0.f; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; b += red[1][i]; }
+    atomicAdd(&sc->loss_sum, a);
+    atomicAdd(&sc->pos_count, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. CSC build: feat_count (float, from k_topk) -> offsets (exclusive scan) ; fill entries
+__global__ void __launch_bounds__(1024) k_scan_counts(const float* __restrict__ cnt, int* __restrict__ off, int* __restrict__ cursor, int F) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  const int per = (F + 1023) / 1024;
+  const int a = t * per, b = min(F, a + per);
+  int s = 0;
+  for (int i = a; i < b; ++i) s += (int)cnt[i];
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    int v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = t ? part[t - 1] : 0;
+  for (int i = a; i < b; ++i) {
+    off[i] = run;
+    cursor[i] = run;
+    run += (int)cnt[i];
+  }
+  if (t == 1023) off[F] = part[1023];
+}
+__global__ void __launch_bounds__(256) k_csc_fill(const int* __restrict__ idx, int* __restrict__ cursor, int* __restrict__ entries, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int f = idx[e];
+    const int pos = atomicAdd(cursor + f, 1);
+    entries[pos] = (int)e;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. per-feature gradients (one warp per feature, persistent grid)
+//    gW_dec[f]  = sum_{tokens b selecting f} relu(val) g[b]          (d loss / d W_dec row)
+//    gW_encT[f] = sum dval * sae_in[b]                                (d loss / d W_enc column)
+//    gb_enc[f]  = sum dval
+//    gbdec2    += gb_enc[f] * W_encT[f]     (the -b_dec path through sae_in = xn - b_dec: d sae_in = W_enc dpre)
+//    fired[f]   = number of tokens with relu(val) > 0 ; gnorm_sq += all squares
+// Entry order inside a feature list comes from atomics, so the fp32 sums are order-nondeterministic at the
+// 1e-7 level; the list is therefore sorted by token index first (lists are short: mean Bt*k/F).
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, int* __restrict__ entries, const float* __restrict__ val,
+                                                   const float* __restrict__ dval, const float* __restrict__ g, const float* __restrict__ sae_in,
+                                                   const float* __restrict__ W_encT, float* __restrict__ gW_dec, float* __restrict__ gW_encT,
+                                                   float* __restrict__ gb_enc, float* __restrict__ gbdec2, float* __restrict__ fired,
+                                                   SaeScalars* __restrict__ sc, int F, int d, int k) {
+  extern __shared__ __align__(16) float sm_bd[];  // [d] per-CTA partial of gbdec2
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nvec = d >> 2;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) sm_bd[c] = 0.f;
+  __syncthreads();
+  float nsq = 0.f;
+  for (int f = blockIdx.x * nw + warp; f < F; f += gridDim.x * nw) {
+    const int e0 = off[f], e1 = off[f + 1];
+    // sort the (short) entry list by flat index == by token: insertion sort by lane 0 for tiny lists,
+    // odd-even transposition across lanes would be overkill here
+    const int len = e1 - e0;
+    if (len > 1 && len <= 64) {
+      if (lane == 0) {
+        for (int i = e0 + 1; i < e1; ++i) {
+          const int key = entries[i];
+          int j = i - 1;
+          while (j >= e0 && entries[j] > key) { entries[j + 1] = entries[j]; --j; }
+          entries[j + 1] = key;
+        }
+      }
+      __syncwarp();
+    }
+    float ad[CHUNKS][4], ae[CHUNKS][4];
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) ad[i][0] = ad[i][1] = ad[i][2] = ad[i][3] = ae[i][0] = ae[i][1] = ae[i][2] = ae[i][3] = 0.f;
+    float gbe = 0.f, npos = 0.f;
+    for (int p = e0; p < e1; ++p) {
+      const int e = entries[p];
+      const int b = e / k;
+      const float a = fmaxf(val[e], 0.f);
+      const float dp = dval[e];
+      if (a > 0.f) npos += 1.f;
+      gbe += dp;
+      const float* gr = g + (int64_t)b * d;
+      const float* sr = sae_in + (int64_t)b * d;
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c4 = i * 32 + lane;
+        if (c4 < nvec) {
+          float gv[4], sv[4];
+          ld4(gr + 4 * c4, gv);
+          ld4(sr + 4 * c4, sv);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { ad[i][q] = fmaf(a, gv[q], ad[i][q]); ae[i][q] = fmaf(dp, sv[q], ae[i][q]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        st4(gW_dec + (int64_t)f * d + 4 * c4, ad[i]);
+        st4(gW_encT + (int64_t)f * d + 4 * c4, ae[i]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nsq += ad[i][q] * ad[i][q] + ae[i][q] * ae[i][q];
+        if (gbe != 0.f) {
+          float w[4];
+          ld4(W_encT + (int64_t)f * d + 4 * c4, w);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) atomicAdd(&sm_bd[4 * c4 + q], gbe * w[q]);
+        }
+      }
+    }
+    if (lane == 0) {
+      gb_enc[f] = gbe;
+      fired[f] = npos;
+      nsq += gbe * gbe;
+    }
+  }
+  nsq = warp_sum(nsq);
+  __shared__ float red[8];
+  if (lane == 0) red[warp] = nsq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < nw; ++i) a += red[i];
+    atomicAdd(&sc->gnorm_sq, a);
+  }
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    if (sm_bd[c] != 0.f) atomicAdd(gbdec2 + c, sm_bd[c]);
+}
+
+// 6. finalize: gb_dec = colsum(g) - gbdec2 ; total norm ; clip coefficient (train_sae.py:394-397)
+__global__ void __launch_bounds__(256) k_sae_finalize(const float* __restrict__ gcol, const float* __restrict__ gbdec2, float* __restrict__ gb_dec,
+                                                      SaeScalars* __restrict__ sc, int d, float max_norm, float inv_elems, float inv_rows) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = gcol[c] - gbdec2[c];
+    gb_dec[c] = v;
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = sc->gnorm_sq;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    const float norm = sqrtf(t);
+    sc->gnorm_sq = t;
+    sc->grad_norm = norm;
+    sc->clip_coef = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+    sc->mse = sc->loss_sum * inv_elems;
+    sc->l0 = sc->pos_count * inv_rows;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 7. optimizer: clip -> remove decoder-parallel gradient -> Adam -> unit-norm decoder rows (+ counters)
+//    (train_sae.py:394-401, sae.py:275-297, torch.optim.Adam defaults betas (0.9, 0.999), eps 1e-8, no weight decay)
+//    The row renorm is the *next* step's set_decoder_norm_to_unit_norm() (train_sae.py:307) applied early; forward
+//    and backward of every later step see identical numbers.
+struct AdamHyper { float lr, beta1, beta2, eps, bc1, bc2_sqrt; };  // bc1 = 1-beta1^t, bc2_sqrt = sqrt(1-beta2^t)
+
+__device__ __forceinline__ float adam_update(float p, float gr, float& m, float& v, const AdamHyper& h) {
+  m = h.beta1 * m + (1.f - h.beta1) * gr;
+  v = h.beta2 * v + (1.f - h.beta2) * gr * gr;
+  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
+  return p - (h.lr / h.bc1) * (m / denom);
+}
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec, float* __restrict__ W_encT, float* __restrict__ W_encT_lo,
+                                                       float* __restrict__ b_enc, const float* __restrict__ gW_dec,
+                                                       const float* __restrict__ gW_encT, const float* __restrict__ gb_enc,
+                                                       float* __restrict__ m_dec, float* __restrict__ v_dec, float* __restrict__ m_enc,
+                                                       float* __restrict__ v_enc, float* __restrict__ m_be, float* __restrict__ v_be,
+                                                       const float* __restrict__ fired, float* __restrict__ since_fired,
+                                                       float* __restrict__ act_freq, const SaeScalars* __restrict__ sc, AdamHyper h,
+                                                       int F, int d, int renorm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nvec = d >> 2;
+  const float clip = sc->clip_coef;
+  for (int f = blockIdx.x * nw + warp; f < F; f += gridDim.x * nw) {
+    const int64_t base = (int64_t)f * d;
+    // ---- decoder row
+    float w[CHUNKS][4], gq[CHUNKS][4];
+    float par = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        ld4(W_dec + base + 4 * c4, w[i]);
+        ld4(gW_dec + base + 4 * c4, gq[i]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { gq[i][q] *= clip; par = fmaf(gq[i][q], w[i][q], par); }
+      } else {
+        w[i][0] = w[i][1] = w[i][2] = w[i][3] = gq[i][0] = gq[i][1] = gq[i][2] = gq[i][3] = 0.f;
+      }
+    }
+    par = warp_sum(par);
+    float nsq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        float mm[4], vv[4];
+        ld4(m_dec + base + 4 * c4, mm);
+        ld4(v_dec + base + 4 * c4, vv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float gr = gq[i][q] - par * w[i][q];
+          w[i][q] = adam_update(w[i][q], gr, mm[q], vv[q], h);
+          nsq += w[i][q] * w[i][q];
+        }
+        st4(m_dec + base + 4 * c4, mm);
+        st4(v_dec + base + 4 * c4, vv);
+      }
+    }
+    const float nrm = sqrtf(warp_sum(nsq));
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        if (renorm) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[i][q] = w[i][q] / nrm;
+        }
+        st4(W_dec + base + 4 * c4, w[i]);
+      }
+    }
+    // ---- encoder row (feature-major)
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        float p[4], gr[4], mm[4], vv[4], lo[4];
+        ld4(W_encT + base + 4 * c4, p);
+        ld4(gW_encT + base + 4 * c4, gr);
+        ld4(m_enc + base + 4 * c4, mm);
+        ld4(v_enc + base + 4 * c4, vv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          p[q] = adam_update(p[q], gr[q] * clip, mm[q], vv[q], h);
+          lo[q] = p[q] - tf32_trunc(p[q]);
+        }
+        st4(W_encT + base + 4 * c4, p);
+        st4(m_enc + base + 4 * c4, mm);
+        st4(v_enc + base + 4 * c4, vv);
+        if (W_encT_lo) st4(W_encT_lo + base + 4 * c4, lo);
+      }
+    }
+    if (lane == 0) {
+      float mm = m_be[f], vv = v_be[f];
+      b_enc[f] = adam_update(b_enc[f], gb_enc[f] * clip, mm, vv, h);
+      m_be[f] = mm;
+      v_be[f] = vv;
+      // dead-feature bookkeeping (train_sae.py:356-361)
+      if (since_fired) since_fired[f] = fired[f] > 0.f ? 0.f : since_fired[f] + 1.f;
+      if (act_freq) act_freq[f] += fired[f];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sae_adam_vec(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                      float* __restrict__ v, const SaeScalars* __restrict__ sc, AdamHyper h, int n) {
+  const float clip = sc->clip_coef;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float mm = m[i], vv = v[i];
+    p[i] = adam_update(p[i], g[i] * clip, mm, vv, h);
+    m[i] = mm;
+    v[i] = vv;
+  }
+}
+
+// row norms -> unit (set_decoder_norm_to_unit_norm, sae.py:275-277) as a standalone op
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) k_unit_rows(float* __restrict__ W, float* __restrict__ W_lo, int F, int d) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nvec = d >> 2;
+  for (int f = blockIdx.x * nw + warp; f < F; f += gridDim.x * nw) {
+    float w[CHUNKS][4];
+    float nsq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        ld4(W + (int64_t)f * d + 4 * c4, w[i]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nsq += w[i][q] * w[i][q];
+      }
+    }
+    const float nrm = sqrtf(warp_sum(nsq));
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        float lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { w[i][q] = w[i][q] / nrm; lo[q] = w[i][q] - tf32_trunc(w[i][q]); }
+        st4(W + (int64_t)f * d + 4 * c4, w[i]);
+        if (W_lo) st4(W_lo + (int64_t)f * d + 4 * c4, lo);
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static int chunks_for(int d) {
+  if (d % 4 != 0) return -1;
+  const int nvec = d / 4;
+  if (nvec <= 32) return 1;
+  if (nvec <= 64) return 2;
+  if (nvec <= 128) return 4;
+  if (nvec <= 192) return 6;
+  if (nvec <= 256) return 8;
+  if (nvec <= 384) return 12;
+  return -1;
+}
+#define PB_DISPATCH_CHUNKS(CH, CALL)                                                   \
+  switch (CH) {                                                                        \
+    case 1: { constexpr int C_ = 1; CALL; } break;                                     \
+    case 2: { constexpr int C_ = 2; CALL; } break;                                     \
+    case 4: { constexpr int C_ = 4; CALL; } break;                                     \
+    case 6: { constexpr int C_ = 6; CALL; } break;                                     \
+    case 8: { constexpr int C_ = 8; CALL; } break;                                     \
+    case 12: { constexpr int C_ = 12; CALL; } break;                                   \
+    default: pb_set_error("sae: d_in=%d unsupported (needs d %% 4 == 0 and d <= 1536)", d); return PB_EUNSUPPORTED; \
+  }
+
+static int persistent_grid(int warps_per_cta, int items) {
+  int ctas = pb_sm_count() * 4;
+  const int need = (items + warps_per_cta - 1) / warps_per_cta;
+  if (ctas > need) ctas = need;
+  return ctas < 1 ? 1 : ctas;
+}
+
+extern "C" int pb_sae_prep(const float* x, const float* b_dec, float* sae_in, float* sae_in_lo, float* mu, float* sd, float* xsum, int32_t rows,
+                           int32_t d, int32_t norm_mode, pb_stream_t stream) {
+  PB_CHECK_ARG(x && b_dec && sae_in && rows >= 0 && d > 0, "pb_sae_prep: bad arguments");
+  PB_CHECK_ARG(norm_mode == 0 || (mu && sd), "pb_sae_prep: mu/std buffers required when normalising");
+  if (rows == 0) return PB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ch = chunks_for(d);
+  PB_DISPATCH_CHUNKS(ch, (k_sae_prep<C_><<<(rows + 7) / 8, 256, 0, st>>>(x, b_dec, sae_in, sae_in_lo, mu, sd, rows, d, norm_mode, 1e-5f)));
+  PB_LAUNCH_CHECK();
+  if (xsum) {
+    PB_CUDA(cudaMemsetAsync(xsum, 0, sizeof(float) * d, st));
+    const int rpc = 32;
+    k_colsum<<<(rows + rpc - 1) / rpc, 256, 0, st>>>(x, xsum, rows, d, rpc);
+    PB_LAUNCH_CHECK();
+  }
+  return PB_OK;
+}
+
+static int launch_topk(const float* vals, const int* map, int64_t row_stride, int F, int seg_len, int nseg, int k, int* oi, float* ov,
+                       int64_t out_stride, float* feat_count, int rows, cudaStream_t st) {
+  const int ipt_needed = (seg_len + 255) / 256;
+  const int ipt = ipt_needed <= 8 ? 8 : ipt_needed <= 24 ? 24 : ipt_needed <= 48 ? 48 : 96;
+  int cap = ipt * k;
+  if (cap > seg_len) cap = seg_len;
+  if (cap < k) cap = k;
+  const size_t smem = 256 * 8 + (size_t)cap * 8;
+  if (smem > 200 * 1024) { pb_set_error("pb_sae_topk: k=%d too large for the candidate buffer", k); return PB_EUNSUPPORTED; }
+  dim3 grid(rows, nseg);
+#define PB_TOPK(IPT)                                                                                                      \
+  do {                                                                                                                    \
+    auto kern = k_topk<IPT>;                                                                                              \
+    if (smem > 48 * 1024) PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    kern<<<grid, 256, smem, st>>>(vals, map, row_stride, F, seg_len, k, oi, ov, out_stride, feat_count, cap);             \
+  } while (0)
+  if (ipt == 8) PB_TOPK(8);
+  else if (ipt == 24) PB_TOPK(24);
+  else if (ipt == 48) PB_TOPK(48);
+  else PB_TOPK(96);
+#undef PB_TOPK
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// hidden_pre [rows][F] -> idx/val [rows][k]; feat_count[F] (float) += selections; scratch: 2 * rows * nseg * k * 4 bytes
+extern "C" int pb_sae_topk(const float* hidden_pre, int32_t rows, int32_t F, int32_t k, int32_t* idx, float* val, float* feat_count,
+                           void* scratch, int64_t scratch_bytes, pb_stream_t stream) {
+  PB_CHECK_ARG(hidden_pre && idx && val && rows >= 0 && F > 0 && k > 0 && k <= F, "pb_sae_topk: bad arguments");
+  PB_CHECK_ARG(k <= 256, "pb_sae_topk: k=%d > 256 unsupported", k);
+  if (rows == 0) return PB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int SEG = 256 * 96;
+  if (F <= SEG) return launch_topk(hidden_pre, nullptr, F, F, F, 1, k, idx, val, k, feat_count, rows, st);
+  const int nseg = (F + SEG - 1) / SEG;
+  const int seg_len = ((F + nseg - 1) / nseg + 255) / 256 * 256;
+  const int64_t need = (int64_t)rows * nseg * k * 8;
+  PB_CHECK_ARG(scratch && scratch_bytes >= need, "pb_sae_topk: scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)need);
+  int* ci = (int*)scratch;
+  float* cv = (float*)(ci + (int64_t)rows * nseg * k);
+  PB_TRY(launch_topk(hidden_pre, nullptr, F, F, seg_len, nseg, k, ci, cv, (int64_t)nseg * k, nullptr, rows, st));
+  return launch_topk(cv, ci, (int64_t)nseg * k, nseg * k, nseg * k, 1, k, idx, val, k, feat_count, rows, st);
+}
+
+extern "C" int pb_sae_scatter_acts(const int32_t* idx, const float* val, float* dense, int32_t rows, int32_t k, int32_t F, int32_t relu,
+                                   pb_stream_t stream) {
+  PB_CHECK_ARG(idx && val && dense && rows >= 0, "pb_sae_scatter_acts: bad arguments");
+  if (rows == 0) return PB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  PB_CUDA(cudaMemsetAsync(dense, 0, sizeof(float) * (size_t)rows * F, st));
+  k_scatter_acts<<<pb_sm_count() * 4, 256, 0, st>>>(idx, val, dense, rows, k, F, relu);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// PbSaeStep: every pointer of one training / inference step (device memory owned by the caller)
+extern "C" int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream) {
+  PB_CHECK_ARG(s && s->x && s->xsum && s->idx && s->val && s->W_dec && s->b_dec && s->scalars, "pb_sae_decode: missing pointers");
+  PB_CHECK_ARG(!s->training || (s->g && s->dval), "pb_sae_decode: training needs g and dval buffers");
+  if (s->rows == 0) return PB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = s->d, ch = chunks_for(d);
+  PB_DISPATCH_CHUNKS(ch, (k_sae_decode<C_><<<(s->rows + 7) / 8, 256, 0, st>>>(
+      s->x, s->xsum, s->mu, s->sd, s->idx, s->val, s->W_dec, s->b_dec, s->sae_out, s->g, s->dval, (SaeScalars*)s->scalars, s->rows, d, s->k,
+      s->norm_mode, s->training, 1.f / (float)s->rows)));
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream) {
+  PB_CHECK_ARG(s && s->idx && s->val && s->dval && s->g && s->sae_in && s->W_encT && s->feat_count && s->csc_off && s->csc_cursor &&
+               s->csc_entries && s->gW_dec && s->gW_encT && s->gb_enc && s->gb_dec && s->gcol && s->gbdec2 && s->fired && s->scalars,
+               "pb_sae_backward: missing pointers");
+  if (s->rows == 0) return PB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = s->d, F = s->F, ch = chunks_for(d);
+  k_scan_counts<<<1, 1024, 0, st>>>(s->feat_count, s->csc_off, s->csc_cursor, F);
+  PB_LAUNCH_CHECK();
+  const int64_t n = (int64_t)s->rows * s->k;
+  k_csc_fill<<<pb_sm_count() * 4, 256, 0, st>>>(s->idx, s->csc_cursor, s->csc_entries, n);
+  PB_LAUNCH_CHECK();
+  PB_CUDA(cudaMemsetAsync(s->gcol, 0, sizeof(float) * d, st));
+  PB_CUDA(cudaMemsetAsync(s->gbdec2, 0, sizeof(float) * d, st));
+  const int rpc = 32;
+  k_colsum<<<(s->rows + rpc - 1) / rpc, 256, 0, st>>>(s->g, s->gcol, s->rows, d, rpc);
+  PB_LAUNCH_CHECK();
+  const int grid = persistent_grid(8, F);
+  PB_DISPATCH_CHUNKS(ch, (k_sae_grads<C_><<<grid, 256, sizeof(float) * d, st>>>(s->csc_off, s->csc_entries, s->val, s->dval, s->g, s->sae_in,
+                                                                                s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc, s->gbdec2,
+                                                                                s->fired, (SaeScalars*)s->scalars, F, d, s->k)));
+  PB_LAUNCH_CHECK();
+  k_sae_finalize<<<1, 256, 0, st>>>(s->gcol, s->gbdec2, s->gb_dec, (SaeScalars*)s->scalars, d, s->max_grad_norm,
+                                    1.f / ((float)s->rows * (float)d), 1.f / (float)s->rows);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream) {
+  PB_CHECK_ARG(s && s->W_dec && s->W_encT && s->b_enc && s->b_dec && s->gW_dec && s->gW_encT && s->gb_enc && s->gb_dec && s->m_dec &&
+               s->v_dec && s->m_enc && s->v_enc && s->m_be && s->v_be && s->m_bd && s->v_bd && s->fired && s->scalars,
+               "pb_sae_adam: missing pointers");
+  PB_CHECK_ARG(s->step >= 1, "pb_sae_adam: step counter starts at 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = s->d, F = s->F, ch = chunks_for(d);
+  AdamHyper h;
+  h.lr = s->lr; h.beta1 = s->beta1; h.beta2 = s->beta2; h.eps = s->adam_eps;
+  h.bc1 = 1.f - powf(s->beta1, (float)s->step);
+  h.bc2_sqrt = sqrtf(1.f - powf(s->beta2, (float)s->step));
+  const int grid = persistent_grid(8, F);
+  PB_DISPATCH_CHUNKS(ch, (k_sae_adam_rows<C_><<<grid, 256, 0, st>>>(s->W_dec, s->W_encT, s->W_encT_lo, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc,
+                                                                     s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, s->fired,
+                                                                     s->since_fired, s->act_freq, (const SaeScalars*)s->scalars, h,
+                                                                     F, d, s->renorm_decoder)));
+  PB_LAUNCH_CHECK();
+  k_sae_adam_vec<<<(d + 255) / 256, 256, 0, st>>>(s->b_dec, s->gb_dec, s->m_bd, s->v_bd, (const SaeScalars*)s->scalars, h, d);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_unit_norm_rows(float* W, float* W_lo, int32_t F, int32_t d, pb_stream_t stream) {
+  PB_CHECK_ARG(W && F >= 0 && d > 0, "pb_unit_norm_rows: bad arguments");
+  if (F == 0) return PB_OK;
+  const int ch = chunks_for(d);
+  cudaStream_t st = (cudaStream_t)stream;
+  PB_DISPATCH_CHUNKS(ch, (k_unit_rows<C_><<<persistent_grid(8, F), 256, 0, st>>>(W, W_lo, F, d)));
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+int pb_abi_sizeof_sae(int which) {
+  if (which == 6) return (int)sizeof(PbSaeStep);
+  if (which == 7) return (int)sizeof(SaeScalars);
+  return -1;
+}

@@ -1,0 +1,202 @@
+"""TopK-SAE step engine: owns the device buffers of a training step and drives the six C-ABI calls.
+
+    prep -> encoder GEMM (tcgen05 3xTF32 | exact FFMA) -> topk -> decode/loss -> backward -> adam
+
+Stands in for ``StandardSparseAutoencoder.forward`` + ``loss.backward()`` + ``clip_grad_norm_`` +
+``remove_gradient_parallel_to_decoder_directions`` + ``Adam.step`` of the reference
+(sae/sae.py:557-645, sae/train_sae.py:278-411).  Nothing here synchronises with the host: the scalars
+of a step (mse, grad norm, clip coefficient, l0) stay in an 8-float device buffer that callers read
+only when they log.
+
+Parameter storage: the encoder lives feature-major as ``W_encT [F, d]``; the module exposes
+``W_enc`` as the transposed view ``W_encT.t()`` so state dicts keep the reference shape ``[d, F]``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from .ops import _need_cuda, _stream
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class PbSaeStep(C.Structure):
+    _fields_ = (
+        [(n, i32) for n in ("rows", "d", "F", "k", "norm_mode", "training", "step", "renorm_decoder")]
+        + [(n, f32) for n in ("lr", "beta1", "beta2", "adam_eps", "max_grad_norm")]
+        + [(n, vp) for n in (
+            "x", "W_encT", "W_encT_lo", "W_dec", "b_enc", "b_dec",
+            "sae_in", "mu", "sd", "xsum", "idx", "val", "feat_count", "sae_out", "g", "dval",
+            "csc_off", "csc_cursor", "csc_entries", "gW_dec", "gW_encT", "gb_enc", "gb_dec", "gcol", "gbdec2",
+            "fired", "scalars", "m_dec", "v_dec", "m_enc", "v_enc", "m_be", "v_be", "m_bd", "v_bd",
+            "since_fired", "act_freq")]
+    )
+
+
+L.ABI_STRUCTS.append(PbSaeStep)
+L.register_signatures({
+    "pb_sae_prep": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "pb_sae_topk": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, i64, vp]),
+    "pb_sae_scatter_acts": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "pb_sae_decode": (i32, [C.POINTER(PbSaeStep), vp]),
+    "pb_sae_backward": (i32, [C.POINTER(PbSaeStep), vp]),
+    "pb_sae_adam": (i32, [C.POINTER(PbSaeStep), vp]),
+    "pb_unit_norm_rows": (i32, [vp, vp, i32, i32, vp]),
+})
+
+NORM_MODE = {"none": 0, None: 0, "layer_norm": 1, "constant_norm_rescale": 2}
+SCALAR_NAMES = ("loss_sum", "gnorm_sq", "clip_coef", "mse", "l0", "pos_count", "grad_norm", "reserved")
+TOPK_SEG = 256 * 96
+
+
+def unit_norm_rows_(w: torch.Tensor, w_lo: Optional[torch.Tensor] = None) -> None:
+    """In-place ``w /= ||w||_row`` on a contiguous [F, d] fp32 CUDA tensor (+ tf32 residual)."""
+    _need_cuda(w)
+    assert w.is_contiguous() and w.dtype == torch.float32
+    L.check(L.get_lib().pb_unit_norm_rows(w.data_ptr(), None if w_lo is None else w_lo.data_ptr(), w.shape[0], w.shape[1], _stream()),
+            "pb_unit_norm_rows")
+
+
+class SaeStepEngine:
+    """Buffers + launch sequence for one (d, F, k, rows) geometry.  ``train_step`` mutates the parameters in place."""
+
+    def __init__(self, W_encT: torch.Tensor, W_dec: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, k: int,
+                 normalize_activations: str = "layer_norm", max_grad_norm: float = 1.0, betas=(0.9, 0.999), adam_eps: float = 1e-8,
+                 gemm_impl: int = L.GEMM_AUTO):
+        _need_cuda(W_encT, W_dec, b_enc, b_dec)
+        for t in (W_encT, W_dec, b_enc, b_dec):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise L.PrismaB200Error("SaeStepEngine: parameters must be contiguous fp32 CUDA tensors")
+        self.F, self.d = W_dec.shape
+        assert W_encT.shape == (self.F, self.d) and b_enc.shape == (self.F,) and b_dec.shape == (self.d,)
+        self.k = int(k)
+        self.W_encT, self.W_dec, self.b_enc, self.b_dec = W_encT, W_dec, b_enc, b_dec
+        self.norm_mode = NORM_MODE[normalize_activations]
+        self.max_grad_norm = float(max_grad_norm or 0.0)
+        self.betas, self.adam_eps = betas, adam_eps
+        self.gemm_impl = gemm_impl
+        dev = W_dec.device
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
+        self.W_encT_lo = torch.empty_like(W_encT)
+        self.refresh_lo()
+        # optimizer state (torch.optim.Adam: exp_avg / exp_avg_sq start at zero)
+        self.m_dec, self.v_dec, self.m_enc, self.v_enc = z(self.F, self.d), z(self.F, self.d), z(self.F, self.d), z(self.F, self.d)
+        self.m_be, self.v_be, self.m_bd, self.v_bd = z(self.F), z(self.F), z(self.d), z(self.d)
+        # gradients
+        self.gW_dec, self.gW_encT = torch.empty(self.F, self.d, device=dev), torch.empty(self.F, self.d, device=dev)
+        self.gb_enc, self.gb_dec = z(self.F), z(self.d)
+        self.gcol, self.gbdec2, self.xsum = z(self.d), z(self.d), z(self.d)
+        self.feat_count, self.fired = z(self.F), z(self.F)
+        self.csc_off, self.csc_cursor = z(self.F + 1, dt=torch.int32), z(self.F, dt=torch.int32)
+        self.scalars = z(8)
+        self.step_count = 0
+        self._rows = -1
+
+    def refresh_lo(self) -> None:
+        """Recompute the tf32 residual of the encoder (after an external write to the parameters)."""
+        from . import ops
+        self.W_encT_lo.copy_(ops.split_tf32(self.W_encT))
+
+    def _ensure_rows(self, rows: int) -> None:
+        if rows == self._rows:
+            return
+        dev, d, F, k = self.W_dec.device, self.d, self.F, self.k
+        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
+        self.sae_in, self.sae_in_lo, self.g, self.sae_out = e(rows, d), e(rows, d), e(rows, d), e(rows, d)
+        self.mu, self.sd = e(rows), e(rows)
+        self.hidden_pre = e(rows, F)
+        self.idx, self.val, self.dval = e(rows, k, dt=torch.int32), e(rows, k), e(rows, k)
+        self.csc_entries = e(rows * k, dt=torch.int32)
+        nseg = (F + TOPK_SEG - 1) // TOPK_SEG
+        self.topk_scratch = e(max(rows * nseg * k * 8, 16), dt=torch.uint8) if F > TOPK_SEG else None
+        self._rows = rows
+
+    def _desc(self, x: torch.Tensor, training: bool, lr: float = 0.0, since_fired=None, act_freq=None, want_out=True) -> PbSaeStep:
+        s = PbSaeStep()
+        s.rows, s.d, s.F, s.k = x.shape[0], self.d, self.F, self.k
+        s.norm_mode, s.training, s.step, s.renorm_decoder = self.norm_mode, int(training), max(self.step_count, 1), 1
+        s.lr, s.beta1, s.beta2, s.adam_eps, s.max_grad_norm = lr, self.betas[0], self.betas[1], self.adam_eps, self.max_grad_norm
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        s.x = p(x)
+        s.W_encT, s.W_encT_lo, s.W_dec, s.b_enc, s.b_dec = p(self.W_encT), p(self.W_encT_lo), p(self.W_dec), p(self.b_enc), p(self.b_dec)
+        s.sae_in, s.mu, s.sd, s.xsum = p(self.sae_in), p(self.mu), p(self.sd), p(self.xsum)
+        s.idx, s.val, s.feat_count = p(self.idx), p(self.val), p(self.feat_count)
+        s.sae_out, s.g, s.dval = (p(self.sae_out) if want_out else None), p(self.g), p(self.dval)
+        s.csc_off, s.csc_cursor, s.csc_entries = p(self.csc_off), p(self.csc_cursor), p(self.csc_entries)
+        s.gW_dec, s.gW_encT, s.gb_enc, s.gb_dec = p(self.gW_dec), p(self.gW_encT), p(self.gb_enc), p(self.gb_dec)
+        s.gcol, s.gbdec2, s.fired, s.scalars = p(self.gcol), p(self.gbdec2), p(self.fired), p(self.scalars)
+        s.m_dec, s.v_dec, s.m_enc, s.v_enc = p(self.m_dec), p(self.v_dec), p(self.m_enc), p(self.v_enc)
+        s.m_be, s.v_be, s.m_bd, s.v_bd = p(self.m_be), p(self.v_be), p(self.m_bd), p(self.v_bd)
+        s.since_fired, s.act_freq = p(since_fired), p(act_freq)
+        return s
+
+    # ------------------------------------------------------------------ pieces
+    def encode_topk(self, x: torch.Tensor) -> None:
+        """prep + encoder GEMM + topk; fills sae_in, mu, sd, xsum, hidden_pre, idx, val, feat_count."""
+        lib, st = L.get_lib(), _stream()
+        rows = x.shape[0]
+        self._ensure_rows(rows)
+        use_tc = self.gemm_impl != L.GEMM_SIMT
+        L.check(lib.pb_sae_prep(x.data_ptr(), self.b_dec.data_ptr(), self.sae_in.data_ptr(),
+                                self.sae_in_lo.data_ptr() if use_tc else None, self.mu.data_ptr(), self.sd.data_ptr(),
+                                self.xsum.data_ptr(), rows, self.d, self.norm_mode, st), "pb_sae_prep")
+        g = L.PbGemm()
+        g.M, g.N, g.K, g.dtype, g.impl = rows, self.F, self.d, L.PB_F32, self.gemm_impl
+        g.A, g.lda, g.B, g.ldb = self.sae_in.data_ptr(), self.d, self.W_encT.data_ptr(), self.d
+        if use_tc:
+            g.A_lo, g.B_lo = self.sae_in_lo.data_ptr(), self.W_encT_lo.data_ptr()
+        g.bias, g.out0, g.ld0 = self.b_enc.data_ptr(), self.hidden_pre.data_ptr(), self.F
+        L.check(lib.pb_gemm(C.byref(g), st), "pb_gemm(encoder)")
+        self.feat_count.zero_()
+        scratch = self.topk_scratch
+        L.check(lib.pb_sae_topk(self.hidden_pre.data_ptr(), rows, self.F, self.k, self.idx.data_ptr(), self.val.data_ptr(),
+                                self.feat_count.data_ptr(), None if scratch is None else scratch.data_ptr(),
+                                0 if scratch is None else scratch.numel(), st), "pb_sae_topk")
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, want_out: bool = True):
+        """Inference: encode -> topk -> decode -> mse.  Returns (sae_out | None, idx, val); scalars[3] = mse."""
+        _need_cuda(x)
+        x = x.contiguous().float()
+        self.encode_topk(x)
+        self.scalars.zero_()
+        s = self._desc(x, training=False, want_out=want_out)
+        L.check(L.get_lib().pb_sae_decode(C.byref(s), _stream()), "pb_sae_decode")
+        return (self.sae_out if want_out else None), self.idx, self.val
+
+    @torch.no_grad()
+    def train_step(self, x: torch.Tensor, lr: float, since_fired: Optional[torch.Tensor] = None,
+                   act_freq: Optional[torch.Tensor] = None, want_out: bool = False) -> torch.Tensor:
+        """One optimizer step on batch ``x`` [rows, d].  Returns the 8-float device scalars buffer (no sync)."""
+        _need_cuda(x)
+        x = x.contiguous().float()
+        lib, st = L.get_lib(), _stream()
+        self.encode_topk(x)
+        self.scalars.zero_()
+        self.step_count += 1
+        s = self._desc(x, training=True, lr=float(lr), since_fired=since_fired, act_freq=act_freq, want_out=want_out)
+        L.check(lib.pb_sae_decode(C.byref(s), st), "pb_sae_decode")
+        L.check(lib.pb_sae_backward(C.byref(s), st), "pb_sae_backward")
+        L.check(lib.pb_sae_adam(C.byref(s), st), "pb_sae_adam")
+        return self.scalars
+
+    def dense_feature_acts(self) -> torch.Tensor:
+        """feature_acts [rows, F] of the last encode (zeros.scatter_(idx, relu(val)))."""
+        rows = self.idx.shape[0]
+        dense = torch.empty(rows, self.F, device=self.W_dec.device)
+        L.check(L.get_lib().pb_sae_scatter_acts(self.idx.data_ptr(), self.val.data_ptr(), dense.data_ptr(), rows, self.k, self.F, 1,
+                                                _stream()), "pb_sae_scatter_acts")
+        return dense
+
+    def scalars_dict(self) -> dict:
+        """Host read (synchronises): for logging / tests only."""
+        vals = self.scalars.tolist()
+        return dict(zip(SCALAR_NAMES, vals))
+
+    # algorithmic HBM bytes of one training step: 80*d*F + 8*Bt*d
+    def algorithmic_bytes(self, rows: int) -> int:
+        return 80 * self.d * self.F + 8 * rows * self.d
