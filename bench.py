@@ -92,10 +92,19 @@ def _dist():
 
 
 def _cpu_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota
+    (the GPU box shows 128 CPUs but cpu.max grants 16; 128 torch threads on 16 CPUs run 150x slower)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
 
 
 # ------------------------------------------------------------------ CPU (oracle port) arm

@@ -245,6 +245,9 @@ PB_API int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream);
 PB_API int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream);
 /* clip -> remove decoder-parallel gradient -> Adam -> decoder row renorm -> dead-feature counters */
 PB_API int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream);
+/* result[0] = mean( (out - x)^2 / ||x - mean_batch(x)||_2,row )  (_compute_mse_loss, sae.py:144-149); xsum_scratch: [d] */
+PB_API int pb_sae_mse(const float* x, const float* out, float* xsum_scratch, float* result, int32_t rows, int32_t d,
+                      pb_stream_t stream);
 /* W[f,:] /= ||W[f,:]|| (set_decoder_norm_to_unit_norm, sae.py:275-277); optional tf32 residual */
 PB_API int pb_unit_norm_rows(float* W, float* W_lo, int32_t F, int32_t d, pb_stream_t stream);
 

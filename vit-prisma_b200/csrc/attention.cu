@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) k_attention(const T* __restrict__ q, cons
           for (int m = 0; m < KPL; ++m) {
             const int j = m * 32 + lane;
             if (j < Tn) {
-              const float s = round_to<T>(acc[m][r] / attn_scale);
+              const float s = round_to<T>(round_to<T>(acc[m][r]) / attn_scale);  // einsum -> tensor, then "/ attn_scale" -> tensor
               acc[m][r] = s;
               if (scores) st_from_float(scores + ob + j, s);
               mx = fmaxf(mx, s);

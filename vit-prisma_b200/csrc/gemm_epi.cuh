@@ -30,7 +30,7 @@ __device__ __forceinline__ void epilogue_store4(const EpiParams& ep, int row, in
       float bb[4];
       ld4(bias + col, bb);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = round_to<T>(acc[j] + bb[j]);
+      for (int j = 0; j < 4; ++j) v[j] = round_to<T>(round_to<T>(acc[j]) + bb[j]);  // einsum result, then "+ b": two bf16 tensors in the reference
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = round_to<T>(acc[j]);
@@ -65,7 +65,7 @@ __device__ __forceinline__ void epilogue_store4(const EpiParams& ep, int row, in
     for (int j = 0; j < 4; ++j) {
       const int c = col + j;
       if (c >= ep.N) break;
-      const float v = round_to<T>(acc[j] + (bias ? ld_as_float(bias + c) : 0.f));
+      const float v = bias ? round_to<T>(round_to<T>(acc[j]) + ld_as_float(bias + c)) : round_to<T>(acc[j]);
       if (ep.n_split > 1) {
         const int blk = c / ep.split_n;
         st_from_float((T*)ep.out_split[blk] + (int64_t)row * ep.ld0 + (c - blk * ep.split_n), v);

@@ -215,25 +215,56 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ 
     }
   } else {
     // ===================== epilogue =====================
+    // TMEM hands each thread one accumulator ROW (32 consecutive columns per tcgen05.ld); storing from that layout
+    // makes every warp store touch 32 different rows (measured: ~190 GB/s).  So each 32x32 chunk is transposed through
+    // shared memory (the operand ring is idle once "accumulator ready" fired) and written row by row: one warp
+    // instruction = 32 consecutive columns of one row = one full 128-byte line (fp32), bias / activation / residual
+    // applied in that coalesced layout, residual reads coalesced too.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + quarter * 32 + lane;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    float* stage = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
+    const T* bias = (const T*)ep.bias;
+    const int row0 = m0 + quarter * 32;
+    const int nrows = min(32, ep.M - row0);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
-      if (row < ep.M) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = n0 + c * 32 + j * 4;
-          if (col < ep.N) {
-            float v[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])};
-            epilogue_store4<T>(ep, row, col, v);
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int col = n0 + c * 32 + lane;
+      if (col < ep.N && nrows > 0) {
+        const bool has_bias = bias != nullptr;
+        const float bv = has_bias ? ld_as_float(bias + col) : 0.f;
+        T* o0 = nullptr;
+        if (ep.n_split > 1) {
+          const int blk = col / ep.split_n;
+          o0 = (T*)ep.out_split[blk] + (col - blk * ep.split_n);
+        } else if (ep.out0) {
+          o0 = (T*)ep.out0 + col;
+        }
+        if (o0) o0 += (int64_t)row0 * ep.ld0;
+        T* o1 = ep.out1 ? (T*)ep.out1 + (int64_t)row0 * ep.ld1 + col : nullptr;
+        float* o1lo = ep.out1_lo ? ep.out1_lo + (int64_t)row0 * ep.ld1 + col : nullptr;
+        const T* res = ep.residual ? (const T*)ep.residual + (int64_t)row0 * ep.ldr + col : nullptr;
+        for (int rr = 0; rr < nrows; ++rr) {
+          const float a = stage[rr * 33 + lane];
+          const float v = has_bias ? round_to<T>(round_to<T>(a) + bv) : round_to<T>(a);
+          if (o0) { st_from_float(o0, v); o0 += ep.ld0; }
+          if (o1) {
+            float o;
+            if (res) { o = ld_as_float(res) + v; res += ep.ldr; }
+            else o = apply_act(v, ep.act);
+            st_from_float(o1, o);
+            o1 += ep.ld1;
+            if (o1lo) { *o1lo = o - tf32_trunc(o); o1lo += ep.ld1; }
           }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();

@@ -808,6 +808,42 @@ extern "C" int pb_unit_norm_rows(float* W, float* W_lo, int32_t F, int32_t d, pb
   return PB_OK;
 }
 
+// normalised MSE of an arbitrary reconstruction (dense / hooked route of SparseAutoencoder.forward, sae.py:144-149)
+__global__ void __launch_bounds__(256) k_sae_mse_rows(const float* __restrict__ x, const float* __restrict__ xsum, const float* __restrict__ out,
+                                                      float* __restrict__ acc, int rows, int d, float inv_rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  float part = 0.f;
+  if (row < rows) {
+    float nsq = 0.f, esq = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float xv = x[(int64_t)row * d + c];
+      const float xc = xv - xsum[c] * inv_rows;
+      const float e = out[(int64_t)row * d + c] - xv;
+      nsq += xc * xc;
+      esq += e * e;
+    }
+    part = warp_sum(esq) / sqrtf(warp_sum(nsq));
+  }
+  if (lane == 0 && row < rows) atomicAdd(acc, part);
+}
+__global__ void k_scale_scalar(float* v, float s) { v[0] *= s; }
+
+extern "C" int pb_sae_mse(const float* x, const float* out, float* xsum_scratch, float* result, int32_t rows, int32_t d, pb_stream_t stream) {
+  PB_CHECK_ARG(x && out && xsum_scratch && result && rows > 0 && d > 0, "pb_sae_mse: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  PB_CUDA(cudaMemsetAsync(xsum_scratch, 0, sizeof(float) * d, st));
+  PB_CUDA(cudaMemsetAsync(result, 0, sizeof(float), st));
+  const int rpc = 32;
+  k_colsum<<<(rows + rpc - 1) / rpc, 256, 0, st>>>(x, xsum_scratch, rows, d, rpc);
+  PB_LAUNCH_CHECK();
+  k_sae_mse_rows<<<(rows + 7) / 8, 256, 0, st>>>(x, xsum_scratch, out, result, rows, d, 1.f / (float)rows);
+  PB_LAUNCH_CHECK();
+  k_scale_scalar<<<1, 1, 0, st>>>(result, 1.f / ((float)rows * (float)d));
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
 int pb_abi_sizeof_sae(int which) {
   if (which == 6) return (int)sizeof(PbSaeStep);
   if (which == 7) return (int)sizeof(SaeScalars);

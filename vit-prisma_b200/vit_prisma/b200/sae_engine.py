@@ -46,6 +46,7 @@ L.register_signatures({
     "pb_sae_backward": (i32, [C.POINTER(PbSaeStep), vp]),
     "pb_sae_adam": (i32, [C.POINTER(PbSaeStep), vp]),
     "pb_unit_norm_rows": (i32, [vp, vp, i32, i32, vp]),
+    "pb_sae_mse": (i32, [vp, vp, vp, vp, i32, i32, vp]),
 })
 
 NORM_MODE = {"none": 0, None: 0, "layer_norm": 1, "constant_norm_rescale": 2}
@@ -59,6 +60,54 @@ def unit_norm_rows_(w: torch.Tensor, w_lo: Optional[torch.Tensor] = None) -> Non
     assert w.is_contiguous() and w.dtype == torch.float32
     L.check(L.get_lib().pb_unit_norm_rows(w.data_ptr(), None if w_lo is None else w_lo.data_ptr(), w.shape[0], w.shape[1], _stream()),
             "pb_unit_norm_rows")
+
+
+def sae_prep(x2: torch.Tensor, b_dec: torch.Tensor, norm_mode: str):
+    """(norm_in(x) - b_dec, mu [rows], std [rows]) for a contiguous fp32 [rows, d] CUDA tensor."""
+    _need_cuda(x2, b_dec)
+    rows, d = x2.shape
+    sae_in = torch.empty_like(x2)
+    mu = torch.empty(rows, device=x2.device)
+    sd = torch.empty(rows, device=x2.device)
+    L.check(L.get_lib().pb_sae_prep(x2.data_ptr(), b_dec.data_ptr(), sae_in.data_ptr(), None, mu.data_ptr(), sd.data_ptr(), None,
+                                    rows, d, NORM_MODE[norm_mode], _stream()), "pb_sae_prep")
+    return sae_in, mu, sd
+
+
+def topk_support(hidden_pre2: torch.Tensor, k: int):
+    """torch.topk(hidden_pre, k, -1) on the GPU: (idx int32 [rows,k], val [rows,k]) sorted by value descending."""
+    _need_cuda(hidden_pre2)
+    rows, F = hidden_pre2.shape
+    idx = torch.empty(rows, k, dtype=torch.int32, device=hidden_pre2.device)
+    val = torch.empty(rows, k, device=hidden_pre2.device)
+    nseg = (F + TOPK_SEG - 1) // TOPK_SEG
+    scratch = torch.empty(max(rows * nseg * k * 8, 16), dtype=torch.uint8, device=hidden_pre2.device) if F > TOPK_SEG else None
+    L.check(L.get_lib().pb_sae_topk(hidden_pre2.data_ptr(), rows, F, k, idx.data_ptr(), val.data_ptr(), None,
+                                    None if scratch is None else scratch.data_ptr(), 0 if scratch is None else scratch.numel(),
+                                    _stream()), "pb_sae_topk")
+    return idx, val
+
+
+def topk_dense(x: torch.Tensor, k: int) -> torch.Tensor:
+    """The TopK activation module's output: zeros_like(x).scatter_(-1, topk idx, relu(topk values))."""
+    _need_cuda(x)
+    lead, F = x.shape[:-1], x.shape[-1]
+    x2 = x.reshape(-1, F).contiguous().float()
+    idx, val = topk_support(x2, k)
+    dense = torch.empty_like(x2)
+    L.check(L.get_lib().pb_sae_scatter_acts(idx.data_ptr(), val.data_ptr(), dense.data_ptr(), x2.shape[0], k, F, 1, _stream()),
+            "pb_sae_scatter_acts")
+    return dense.view(*lead, F).to(x.dtype)
+
+
+def sae_mse(x2: torch.Tensor, out2: torch.Tensor) -> torch.Tensor:
+    """0-dim device tensor: mean((out - x)^2 / ||x - mean_batch(x)||) (sae.py:144-149)."""
+    _need_cuda(x2, out2)
+    rows, d = x2.shape
+    xsum = torch.empty(d, device=x2.device)
+    res = torch.empty(1, device=x2.device)
+    L.check(L.get_lib().pb_sae_mse(x2.data_ptr(), out2.data_ptr(), xsum.data_ptr(), res.data_ptr(), rows, d, _stream()), "pb_sae_mse")
+    return res[0]
 
 
 class SaeStepEngine:

@@ -1,0 +1,335 @@
+"""Sparse autoencoders on the B200 path (reference sae/sae.py:29-839).
+
+``StandardSparseAutoencoder`` keeps the reference surface -- ``encode`` / ``decode`` / ``forward`` (7-tuple),
+``set_decoder_norm_to_unit_norm``, ``initialize_b_dec*``, ``save_model`` / ``load_from_pretrained``, the four
+HookPoints, state-dict keys ``W_enc [d_in,d_sae]``, ``W_dec [d_sae,d_in]``, ``b_enc``, ``b_dec`` -- with two routes:
+
+* **sparse** (TopK, no hooks attached): vit_prisma/b200/sae_engine.py -- prep -> tensor-core encoder GEMM -> exact
+  TopK -> sparse decode + normalised MSE.  The dense ``feature_acts`` the API returns is scattered from the
+  ``[rows, k]`` support only because the signature promises a dense tensor.
+* **dense / hooked** (``encode`` / ``decode`` called directly, ReLU activations, or any hook attached): op by op through
+  the same kernels, every HookPoint fired in the reference order with replace-on-return semantics.
+
+The encoder weight lives feature-major in memory (``W_enc`` is a transposed view of a contiguous ``[d_sae, d_in]``
+buffer): that is the K-major operand the encoder GEMM wants and gives the optimizer one contiguous row per feature,
+while ``state_dict()['W_enc']`` keeps the reference shape.
+
+Training happens in ``VisionSAETrainer`` through the fused step engine (hand-written backward); this module's
+``forward`` does not build an autograd graph.
+"""
+from __future__ import annotations
+
+import gzip
+import logging
+import math
+import os
+import pickle
+from abc import ABC, abstractmethod
+from typing import Any, Callable, Optional
+
+import torch
+from torch import nn
+
+from vit_prisma.b200 import _lib as L
+from vit_prisma.b200 import ops
+from vit_prisma.prisma_tools.hook_point import HookPoint
+from vit_prisma.prisma_tools.hooked_root_module import HookedRootModule
+from vit_prisma.sae.config import VisionModelSAERunnerConfig
+from vit_prisma.sae.training.geometric_median import compute_geometric_median
+
+
+class TopK(nn.Module):
+    """``zeros.scatter_(topk(x, k).indices, postact(topk values))`` (reference :795-808)."""
+
+    def __init__(self, k: int, postact_fn: Callable[[torch.Tensor], torch.Tensor] = nn.ReLU()):
+        super().__init__()
+        self.k = k
+        self.postact_fn = postact_fn
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from vit_prisma.b200.sae_engine import topk_dense
+        if not isinstance(self.postact_fn, nn.ReLU):
+            raise NotImplementedError("TopK on the B200 path supports the default ReLU post-activation")
+        return topk_dense(x, self.k)
+
+
+def get_activation_fn(activation_fn: str, **kwargs: Any) -> Callable[[torch.Tensor], torch.Tensor]:
+    logging.info(f"get_activation_fn received: activation_fn={activation_fn}, kwargs={kwargs}")
+    if activation_fn == "relu":
+        return lambda x: ops.activation(x, "relu")
+    if activation_fn == "tanh-relu":
+        return lambda x: ops.activation(x, "tanh-relu")
+    if activation_fn == "topk":
+        assert "k" in kwargs, "TopK activation function requires a k value."
+        return TopK(kwargs.get("k", 64), kwargs.get("postact_fn", nn.ReLU()))
+    raise ValueError(f"Unknown activation function: {activation_fn}")
+
+
+class SparseAutoencoder(HookedRootModule, ABC):
+    def __init__(self, cfg: VisionModelSAERunnerConfig):
+        super().__init__()
+        self.cfg = cfg
+        self.d_in = cfg.d_in
+        if not isinstance(self.d_in, int):
+            raise ValueError(f"d_in must be an int but was {self.d_in}; {type(self.d_in)}")
+        assert cfg.d_sae is not None
+        self.d_sae = cfg.d_sae
+        self.l1_coefficient = cfg.l1_coefficient
+        self.lp_norm = cfg.lp_norm
+        self.dtype = cfg.dtype
+        self.device = cfg.device
+        self.initialization_method = cfg.initialization_method
+        self.zero_loss = torch.tensor(0.0, dtype=self.dtype, device=self.device)
+        self.initialize_sae_weights()
+        self.hook_sae_in = HookPoint()
+        self.hook_hidden_pre = HookPoint()
+        self.hook_hidden_post = HookPoint()
+        self.hook_sae_out = HookPoint()
+        if cfg.normalize_activations not in ("layer_norm", "constant_norm_rescale"):
+            self._norm_mode = "none"
+        else:
+            self._norm_mode = cfg.normalize_activations
+        self.activation_fn = get_activation_fn(cfg.activation_fn_str, **cfg.activation_fn_kwargs)
+        self._engine = None
+        self.setup()
+
+    # ------------------------------------------------------------------ init helpers
+    def initialize_weights(self, out_features: int, in_features: int) -> torch.Tensor:
+        """Kaiming-uniform(a=sqrt 5) then unit-norm rows (reference :104-130)."""
+        weight = torch.empty(out_features, in_features, dtype=self.dtype, device=self.device)
+        nn.init.kaiming_uniform_(weight, a=math.sqrt(5))
+        with torch.no_grad():
+            weight /= torch.norm(weight, dim=1, keepdim=True)      # one-off init on whatever device cfg names
+        return weight
+
+    @abstractmethod
+    def encode(self, x: torch.Tensor): ...
+
+    @abstractmethod
+    def decode(self, features: torch.Tensor): ...
+
+    @abstractmethod
+    def initialize_sae_weights(self): ...
+
+    @abstractmethod
+    def forward(self, x: torch.Tensor, dead_neuron_mask: torch.Tensor = None): ...
+
+    # ------------------------------------------------------------------ b_dec initialisation (reference :181-242)
+    @torch.no_grad()
+    def initialize_b_dec_with_precalculated(self, origin: torch.Tensor, transcoder_dec_b: torch.Tensor = None):
+        self.b_dec.data = origin.clone().detach().to(dtype=self.dtype, device=self.b_dec.device)
+
+    @torch.no_grad()
+    def initialize_b_dec(self, all_activations: torch.Tensor):
+        method = self.cfg.b_dec_init_method
+        if method == "geometric_median":
+            self.initialize_b_dec_with_geometric_median(all_activations)
+        elif method == "mean":
+            self.initialize_b_dec_with_mean(all_activations)
+        elif method != "zeros":
+            raise ValueError(f"Unexpected b_dec_init_method: {method}")
+
+    @torch.no_grad()
+    def initialize_b_dec_with_geometric_median(self, all_activations: torch.Tensor):
+        out = compute_geometric_median(all_activations, maxiter=100).median
+        logging.info("Reinitializing b_dec with geometric median of activations")
+        self.b_dec.data = out.to(dtype=self.dtype, device=self.b_dec.device)
+
+    @torch.no_grad()
+    def initialize_b_dec_with_mean(self, all_activations: torch.Tensor):
+        logging.info("Reinitializing b_dec with mean of activations")
+        self.b_dec.data = all_activations.mean(dim=0).to(self.dtype).to(self.b_dec.device)
+
+    # ------------------------------------------------------------------ decoder geometry (reference :275-297)
+    @torch.no_grad()
+    def set_decoder_norm_to_unit_norm(self):
+        if self.W_dec.is_cuda and self.W_dec.dtype == torch.float32 and self.W_dec.is_contiguous():
+            from vit_prisma.b200.sae_engine import unit_norm_rows_
+            unit_norm_rows_(self.W_dec.data)
+        else:
+            self.W_dec.data /= torch.norm(self.W_dec.data, dim=1, keepdim=True)
+
+    @torch.no_grad()
+    def remove_gradient_parallel_to_decoder_directions(self):
+        """Kept for API compatibility with hand-rolled training loops that populated ``W_dec.grad`` themselves;
+        VisionSAETrainer fuses this projection into the optimizer kernel."""
+        par = (self.W_dec.grad * self.W_dec.data).sum(dim=1, keepdim=True)
+        self.W_dec.grad -= par * self.W_dec.data
+
+    # ------------------------------------------------------------------ persistence (reference :299-528)
+    def save_model(self, path: str):
+        folder = os.path.dirname(path)
+        if folder:
+            os.makedirs(folder, exist_ok=True)
+        payload = {"cfg": self.cfg, "state_dict": {k: v.contiguous() for k, v in self.state_dict().items()}}
+        if path.endswith(".pt"):
+            torch.save(payload, path)
+        elif path.endswith("pkl.gz"):
+            with gzip.open(path, "wb") as f:
+                pickle.dump(payload, f)
+        else:
+            raise ValueError(f"Unexpected file extension: {path}, supported extensions are .pt and .pkl.gz")
+        print(f"Saved SAE to {path}")
+
+    @classmethod
+    def load_from_pretrained(cls, weights_path: str, current_cfg=None, config_path: Optional[str] = None):
+        if not os.path.isfile(weights_path):
+            raise FileNotFoundError(f"No file found at specified path: {weights_path}")
+        if weights_path.endswith(".pt"):
+            payload = torch.load(weights_path, map_location="cpu", weights_only=False)
+        elif weights_path.endswith(".pkl.gz"):
+            with gzip.open(weights_path, "rb") as f:
+                payload = pickle.load(f)
+        elif weights_path.endswith(".pkl"):
+            with open(weights_path, "rb") as f:
+                payload = pickle.load(f)
+        else:
+            raise ValueError(f"Unexpected file extension: {weights_path}, supported extensions are .pt, .pkl, and .pkl.gz")
+        if config_path is not None:
+            cfg = VisionModelSAERunnerConfig.load_config(config_path)
+        elif isinstance(payload, dict) and "cfg" in payload:
+            cfg = payload["cfg"]
+        else:
+            raise ValueError("No config found: pass config_path or use a checkpoint that embeds 'cfg'")
+        if current_cfg is not None:
+            cfg._device, cfg._dtype = current_cfg._device, current_cfg._dtype
+        state = payload["state_dict"] if isinstance(payload, dict) and "state_dict" in payload else payload
+        instance = cls(cfg)
+        instance.load_state_dict(state)
+        return instance
+
+    def get_name(self) -> str:
+        return f"sparse_autoencoder_{self.cfg.model_name}_{self.cfg.hook_point}_{self.cfg.d_sae}"
+
+
+class StandardSparseAutoencoder(SparseAutoencoder):
+    def initialize_sae_weights(self):
+        self.W_dec = nn.Parameter(self.initialize_weights(self.d_sae, self.d_in))
+        if self.initialization_method == "independent":
+            enc = self.initialize_weights(self.d_in, self.d_sae)          # [d_in, d_sae], rows unit-norm (reference :541)
+            enc_t = enc.t().contiguous()                                   # feature-major storage
+        elif self.initialization_method == "encoder_transpose_decoder":
+            enc_t = self.W_dec.data.clone()
+        else:
+            raise ValueError(f"Unknown initialization method: {self.initialization_method}")
+        self.W_enc = nn.Parameter(enc_t.t())                               # [d_in, d_sae] view, strides (1, d_in)
+        self.b_enc = nn.Parameter(torch.zeros(self.d_sae, dtype=self.dtype, device=self.device))
+        self.b_dec = nn.Parameter(torch.zeros(self.d_in, dtype=self.dtype, device=self.device))
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _canonical_params(self):
+        """(W_encT [F,d] contiguous view, W_dec, b_enc, b_dec) -- re-lays W_enc out feature-major if something
+        (load_state_dict into a fresh tensor, user assignment) made it row-major."""
+        if not self.W_enc.data.t().is_contiguous():
+            self.W_enc.data = self.W_enc.data.t().contiguous().t()
+        if not self.W_dec.data.is_contiguous():
+            self.W_dec.data = self.W_dec.data.contiguous()
+        return self.W_enc.data.t(), self.W_dec.data, self.b_enc.data, self.b_dec.data
+
+    def step_engine(self, gemm_impl: int = L.GEMM_AUTO):
+        """The fused TopK engine bound to this module's parameter storage (rebuilt if the storage moved)."""
+        from vit_prisma.b200.sae_engine import SaeStepEngine
+        if self.cfg.activation_fn_str != "topk":
+            raise NotImplementedError("the fused step engine covers activation_fn_str == 'topk'")
+        wt, wd, be, bd = self._canonical_params()
+        eng = self._engine
+        key = (wt.data_ptr(), wd.data_ptr(), be.data_ptr(), bd.data_ptr(), gemm_impl)
+        if eng is None or eng._key != key:
+            eng = SaeStepEngine(wt, wd, be, bd, k=self.cfg.activation_fn_kwargs["k"], normalize_activations=self._norm_mode,
+                                max_grad_norm=self.cfg.max_grad_norm, gemm_impl=gemm_impl)
+            eng._key = key
+            eng._enc_version = self.W_enc._version
+            self._engine = eng
+        return eng
+
+    def _hooks_attached(self) -> bool:
+        return not all(hp.is_inert for hp in self.hook_points())
+
+    # ------------------------------------------------------------------ dense / hooked route
+    def _norm_in(self, x2: torch.Tensor):
+        """run_time_activation_norm_fn_in: returns (x_normalised - 0, mu, std) using the prep kernel with a zero bias."""
+        from vit_prisma.b200.sae_engine import sae_prep
+        return sae_prep(x2, torch.zeros_like(self.b_dec.data), self._norm_mode)
+
+    def encode(self, x: torch.Tensor, return_hidden_pre: bool = False):
+        from vit_prisma.b200.sae_engine import sae_prep
+        x = ops.cast(x, self.dtype) if x.dtype != self.dtype else x
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.d_in).contiguous()
+        wt, wd, be, bd = self._canonical_params()
+        sae_in2, mu, sd = sae_prep(x2, bd, self._norm_mode)               # norm_in(x) - b_dec  (reference :560-566)
+        self.ln_mu, self.ln_std = mu.view(*lead, 1), sd.view(*lead, 1)
+        sae_in = self.hook_sae_in(sae_in2.view(*lead, self.d_in))
+        hidden_pre, _ = ops.gemm(sae_in, wt, be)                           # sae_in @ W_enc + b_enc  (:568-574)
+        hidden_pre = self.hook_hidden_pre(hidden_pre)
+        feature_acts = self.hook_hidden_post(self.activation_fn(hidden_pre))
+        if return_hidden_pre:
+            return sae_in, feature_acts, hidden_pre
+        return sae_in, feature_acts
+
+    def decode(self, features: torch.Tensor):
+        wt, wd, be, bd = self._canonical_params()
+        wd_nk = wd.t().contiguous()                                        # [d_in, d_sae]: K-major operand of features @ W_dec
+        out, _ = ops.gemm(features, wd_nk, bd)                             # (:584-592)
+        out = self.hook_sae_out(out)
+        if self._norm_mode == "layer_norm":                                 # x * std + mu  (:89-90)
+            out = ops.add(ops.mul(out, self.ln_std.expand_as(out)), self.ln_mu.expand_as(out))
+        elif self._norm_mode == "constant_norm_rescale":
+            out = ops.mul(out, self.ln_std.expand_as(out))
+        return out
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, dead_neuron_mask: torch.Tensor = None, *args, **kwargs):
+        if self.cfg.use_ghost_grads and self.training and dead_neuron_mask is not None and bool(dead_neuron_mask.any()):
+            raise NotImplementedError("ghost-grad auxiliary loss is not built on the B200 path yet (SURVEY 8a b8)")
+        from vit_prisma.b200.sae_engine import sae_mse
+        lead = x.shape[:-1]
+        x32 = ops.cast(x, self.dtype) if x.dtype != self.dtype else x
+        x2 = x32.reshape(-1, self.d_in).contiguous()
+        sparse_ok = self.cfg.activation_fn_str == "topk" and not self._hooks_attached() and self.dtype == torch.float32
+        if sparse_ok:
+            eng = self.step_engine()
+            if eng._enc_version != self.W_enc._version:                    # parameters written outside the engine
+                eng.refresh_lo()
+                eng._enc_version = self.W_enc._version
+            sae_out2, _idx, _val = eng.forward(x2)
+            sae_out = sae_out2.clone().view(*lead, self.d_in)
+            mse_loss = eng.scalars[3].clone()
+            if getattr(self.cfg, "return_out_only", False):
+                return sae_out
+            feature_acts = eng.dense_feature_acts().view(*lead, self.d_sae)
+        else:
+            _, feature_acts, _hidden_pre = self.encode(x32, return_hidden_pre=True)
+            sae_out = self.decode(feature_acts)
+            if getattr(self.cfg, "return_out_only", False):
+                return sae_out
+            mse_loss = sae_mse(x2, sae_out.reshape(-1, self.d_in).contiguous())
+        if self.cfg.activation_fn_str != "topk":
+            # sparsity = ||feature_acts||_p over dim 1, mean over dim 0 (reference :617; tiny reduction, host-side glue)
+            sparsity = feature_acts.norm(p=self.lp_norm, dim=1).mean(dim=(0,))
+            l1_loss = self.l1_coefficient * sparsity
+            loss = mse_loss + l1_loss
+        else:
+            l1_loss = None
+            loss = mse_loss.clone()
+        return (sae_out, feature_acts, loss, mse_loss, l1_loss, self.zero_loss.to(sae_out.device), torch.tensor(0.0))
+
+
+class GatedSparseAutoencoder(SparseAutoencoder):
+    """Gated SAE (reference :648-792) -- listed as the next row after Standard; not built yet."""
+
+    def __init__(self, cfg):
+        raise NotImplementedError("GatedSparseAutoencoder is outside the round-1 B200 hot-path scope (SURVEY 8f, row f3)")
+
+    def encode(self, x):  # pragma: no cover
+        raise NotImplementedError
+
+    def decode(self, features):  # pragma: no cover
+        raise NotImplementedError
+
+    def initialize_sae_weights(self):  # pragma: no cover
+        raise NotImplementedError
+
+    def forward(self, x, dead_neuron_mask=None):  # pragma: no cover
+        raise NotImplementedError

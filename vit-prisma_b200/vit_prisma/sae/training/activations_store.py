@@ -1,0 +1,197 @@
+"""Activation supply for SAE training (reference sae/training/activations_store.py:21-574).
+
+``VisionActivationsStore`` keeps the reference's interface and mixing semantics -- a storage half-buffer, refills of
+``n_batches_in_buffer // 2`` image batches through ``model.run_with_cache(names_filter=[hook], stop_at_layer=layer+1)``,
+concatenate + ``randperm`` shuffle, keep half, serve half -- with two B200-minded changes:
+
+* refills hit the fused ViT chain with a one-key ``names_filter`` (nothing but the requested hook point is spilled,
+  blocks after the hook layer are never launched);
+* the serving side is a device-resident tensor walked through a ``randperm`` index: ``next_batch`` is one gather, not the
+  reference's ``DataLoader(tensor, shuffle=True)`` whose default collate stacks 4096 single-row tensors in Python
+  (activations_store.py:486-490).
+
+``SyntheticActivationsStore`` serves seeded random activations of the same shape contract (bench / tests / no dataset).
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Iterator, Optional
+
+import torch
+from torch.utils.data import DataLoader
+
+
+def collate_fn(data):
+    return torch.stack([d[0] for d in data], dim=0)
+
+
+def collate_fn_eval(data):
+    return torch.stack([d[0] for d in data], dim=0), torch.tensor([d[1] for d in data])
+
+
+class _ShuffledServer:
+    """Serve ``[n, ...]`` rows in a fresh random order, ``batch`` at a time (drops nothing: last batch may be short)."""
+
+    def __init__(self, data: torch.Tensor, batch: int):
+        self.data, self.batch = data, batch
+        self.perm = torch.randperm(data.shape[0], device=data.device)
+        self.pos = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> torch.Tensor:
+        if self.pos >= self.data.shape[0]:
+            raise StopIteration
+        sel = self.perm[self.pos:self.pos + self.batch]
+        self.pos += self.batch
+        return self.data.index_select(0, sel)
+
+
+class VisionActivationsStore:
+    def __init__(self, cfg, model, dataset, create_dataloader: bool = True, eval_dataset=None, num_workers: int = 0):
+        self.cfg = cfg
+        self.model = model.to(cfg.device)
+        self.dataset = dataset
+        self.image_dataloader = DataLoader(dataset, shuffle=True, num_workers=num_workers, batch_size=cfg.store_batch_size,
+                                           collate_fn=collate_fn, drop_last=True)
+        if eval_dataset is not None:
+            self.image_dataloader_eval = DataLoader(eval_dataset, shuffle=True, num_workers=num_workers,
+                                                    batch_size=cfg.store_batch_size, collate_fn=collate_fn_eval, drop_last=True)
+            self.image_dataloader_eval_iter = self._eval_batch_stream(self.image_dataloader_eval, cfg.device)
+        self.image_dataloader_iter = self._batch_stream(self.image_dataloader, cfg.device)
+        if create_dataloader:
+            if cfg.is_transcoder:
+                raise NotImplementedError("transcoder activation pairs are outside the round-1 scope (SURVEY 8f f3)")
+            self.storage_buffer = self.get_buffer(cfg.n_batches_in_buffer)
+            self.dataloader = self.get_data_loader()
+
+    @staticmethod
+    def _batch_stream(dataloader: DataLoader, device) -> Iterator[torch.Tensor]:
+        while True:
+            for batch in dataloader:
+                batch.requires_grad_(False)
+                yield batch.to(device, non_blocking=True)
+
+    @staticmethod
+    def _eval_batch_stream(dataloader: DataLoader, device):
+        while True:
+            for images, labels in dataloader:
+                yield images.to(device), labels.to(device)
+
+    def _layers(self):
+        hp = self.cfg.hook_point_layer
+        return hp if isinstance(hp, list) else [hp]
+
+    @torch.no_grad()
+    def get_activations(self, batch_images: torch.Tensor) -> torch.Tensor:
+        """[b, T', n_layers, d_in] for the configured hook point(s) (reference :252-296)."""
+        layers = self._layers()
+        names = [self.cfg.hook_point.format(layer=layer) for layer in layers]
+        _, cache = self.model.run_with_cache(batch_images, names_filter=names, stop_at_layer=max(layers) + 1)
+        per_layer = []
+        for name in names:
+            acts = cache[name]
+            if self.cfg.hook_point_head_index is not None:
+                acts = acts[:, :, self.cfg.hook_point_head_index]
+            if self.cfg.cls_token_only:
+                acts = acts[:, 0:1]
+            per_layer.append(acts)
+        return torch.stack(per_layer, dim=2)
+
+    def get_buffer(self, n_batches_in_buffer: int) -> torch.Tensor:
+        cfg = self.cfg
+        if cfg.use_cached_activations:
+            return self._load_cached_activations(cfg.store_batch_size * n_batches_in_buffer, cfg.context_size, len(self._layers()), cfg.d_in)
+        chunks = []
+        for _ in range(n_batches_in_buffer):
+            acts = self.get_activations(next(self.image_dataloader_iter))
+            if cfg.use_patches_only:
+                acts = acts[:, 1:, :, :]
+            chunks.append(acts.reshape(-1, acts.shape[2], cfg.d_in).to(cfg.dtype))
+        buf = torch.cat(chunks, dim=0)
+        return buf[torch.randperm(buf.shape[0], device=buf.device)]
+
+    def _load_cached_activations(self, total_size, context_size, num_layers, d_in) -> torch.Tensor:
+        """fp16/fp32 ``{idx}.pt`` shards of ``[tokens, n_layers, d_in]`` (reference :371-415)."""
+        want = total_size * context_size
+        parts, have, idx = [], 0, 0
+        while have < want:
+            path = f"{self.cfg.cached_activations_path}/{idx}.pt"
+            if not os.path.exists(path):
+                break
+            acts = torch.load(path, map_location=self.cfg.device, weights_only=True)[: want - have]
+            parts.append(acts.to(self.cfg.dtype))
+            have += acts.shape[0]
+            idx += 1
+        if not parts:
+            return torch.zeros((0, num_layers, d_in), dtype=self.cfg.dtype, device=self.cfg.device)
+        return torch.cat(parts, dim=0)
+
+    def get_data_loader(self) -> Iterator[Any]:
+        half = self.cfg.n_batches_in_buffer // 2
+        mixing = torch.cat([self.get_buffer(half), self.storage_buffer], dim=0)
+        mixing = mixing[torch.randperm(mixing.shape[0], device=mixing.device)]
+        keep = mixing.shape[0] // 2
+        self.storage_buffer = mixing[:keep]
+        return _ShuffledServer(mixing[keep:], self.cfg.train_batch_size)
+
+    def next_batch(self) -> torch.Tensor:
+        try:
+            return next(self.dataloader)
+        except StopIteration:
+            self.dataloader = self.get_data_loader()
+            return next(self.dataloader)
+
+
+class SyntheticActivationsStore:
+    """``next_batch()`` -> ``[train_batch_size, 1, d_in]`` seeded synthetic residual-stream-like activations
+    (randn * 2 + per-feature offset: non-zero mean so b_dec init, layer-norm and batch centring all matter).
+    Keeps a device-resident pool and serves shuffled windows of it."""
+
+    def __init__(self, cfg, pool_tokens: int = 1 << 18, seed: int = 0, device=None):
+        self.cfg = cfg
+        dev = torch.device(device) if device is not None else cfg.device
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        offset = torch.randn(cfg.d_in, generator=g)
+        pool = torch.randn(pool_tokens, cfg.d_in, generator=g) * 2.0 + offset
+        self.storage_buffer = pool.to(dev).unsqueeze(1)          # [tokens, n_layers=1, d_in]
+        self.dataloader = _ShuffledServer(self.storage_buffer, cfg.train_batch_size)
+
+    def next_batch(self) -> torch.Tensor:
+        try:
+            batch = next(self.dataloader)
+        except StopIteration:
+            self.dataloader = _ShuffledServer(self.storage_buffer, self.cfg.train_batch_size)
+            batch = next(self.dataloader)
+        if batch.shape[0] < self.cfg.train_batch_size:            # keep the step shape fixed
+            self.dataloader = _ShuffledServer(self.storage_buffer, self.cfg.train_batch_size)
+            batch = next(self.dataloader)
+        return batch
+
+
+class CacheVisionActivationStore:
+    """Serve pre-computed activation shards from ``cfg.cached_activations_path`` (reference :21-152)."""
+
+    def __init__(self, cfg: Any):
+        self.cfg = cfg
+        self.next_cache_idx = 0
+        self.dataloader = self._next_loader()
+
+    def _next_loader(self):
+        path = f"{self.cfg.cached_activations_path}/{self.next_cache_idx}.pt"
+        if not os.path.exists(path):
+            if self.next_cache_idx == 0:
+                raise FileNotFoundError(path)
+            self.next_cache_idx = 0
+            path = f"{self.cfg.cached_activations_path}/0.pt"
+        data = torch.load(path, map_location=self.cfg.device, weights_only=True).to(self.cfg.dtype)
+        self.next_cache_idx += 1
+        return _ShuffledServer(data, self.cfg.train_batch_size)
+
+    def next_batch(self) -> torch.Tensor:
+        try:
+            return next(self.dataloader)
+        except StopIteration:
+            self.dataloader = self._next_loader()
+            return next(self.dataloader)
