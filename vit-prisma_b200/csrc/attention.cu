@@ -16,6 +16,9 @@
 // Arithmetic is fp32; in bf16 mode values are rounded to bf16 exactly where the reference
 // materialises a bf16 tensor (scores, pattern, z).
 #include "common.cuh"
+#include <stdlib.h>
+
+int pb_attention_mma(const PbAttention* p, cudaStream_t st);  // attention_mma.cu
 
 enum { ATT_FUSED = 0, ATT_SCORES = 1, ATT_PV = 2 };
 
@@ -226,6 +229,15 @@ extern "C" int pb_attention(const PbAttention* p, pb_stream_t stream) {
   PB_TRY(check_att(p, "pb_attention"));
   PB_CHECK_ARG(p->q && p->k && p->v && p->z, "pb_attention: q, k, v, z are required");
   if (p->B == 0) return PB_OK;
+  {
+    // d_head == 64, T <= 272: tensor-core kernel (attention_mma.cu); PB_ATTN_IMPL=simt forces the FFMA kernel (cross-check)
+    static int force_simt = -1;
+    if (force_simt < 0) { const char* e = getenv("PB_ATTN_IMPL"); force_simt = (e && !strcmp(e, "simt")) ? 1 : 0; }
+    if (!force_simt) {
+      const int rc = pb_attention_mma(p, (cudaStream_t)stream);
+      if (rc != PB_EUNSUPPORTED) return rc;
+    }
+  }
   return p->dtype == PB_F32 ? launch_att<float, ATT_FUSED>(p, (cudaStream_t)stream) : launch_att<bf16, ATT_FUSED>(p, (cudaStream_t)stream);
 }
 extern "C" int pb_attn_scores(const PbAttention* p, pb_stream_t stream) {

@@ -735,6 +735,11 @@ extern "C" int pb_sae_scatter_acts(const int32_t* idx, const float* val, float* 
 }
 
 // PbSaeStep: every pointer of one training / inference step (device memory owned by the caller)
+__global__ void k_sae_fwd_scalars(SaeScalars* sc, float inv_elems, float inv_rows) {
+  sc->mse = sc->loss_sum * inv_elems;
+  sc->l0 = sc->pos_count * inv_rows;
+}
+
 extern "C" int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream) {
   PB_CHECK_ARG(s && s->x && s->xsum && s->idx && s->val && s->W_dec && s->b_dec && s->scalars, "pb_sae_decode: missing pointers");
   PB_CHECK_ARG(!s->training || (s->g && s->dval), "pb_sae_decode: training needs g and dval buffers");
@@ -745,6 +750,10 @@ extern "C" int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream) {
       s->x, s->xsum, s->mu, s->sd, s->idx, s->val, s->W_dec, s->b_dec, s->sae_out, s->g, s->dval, (SaeScalars*)s->scalars, s->rows, d, s->k,
       s->norm_mode, s->training, 1.f / (float)s->rows)));
   PB_LAUNCH_CHECK();
+  if (!s->training) {  // inference: publish mse / l0 now (the training path does it in k_sae_finalize)
+    k_sae_fwd_scalars<<<1, 1, 0, st>>>((SaeScalars*)s->scalars, 1.f / ((float)s->rows * (float)d), 1.f / (float)s->rows);
+    PB_LAUNCH_CHECK();
+  }
   return PB_OK;
 }
 
