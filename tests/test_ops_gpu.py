@@ -53,7 +53,8 @@ def test_gemm_simt_strided_views():
     assert rel_err(out, ref) < 2e-6
 
 
-TC_SHAPES = [(128, 128, 64), (256, 128, 128), (300, 256, 192), (1000, 768, 768), (512, 2304, 768), (200, 768, 3072), (128, 512, 768)]
+TC_SHAPES = [(128, 128, 64), (256, 128, 128), (300, 256, 192), (1000, 768, 768), (512, 2304, 768), (200, 768, 3072), (128, 512, 768),
+             (260, 384, 128), (5000, 3072, 768), (70, 64, 64)]
 
 
 @pytest.mark.parametrize("M,N,K", TC_SHAPES)
@@ -144,7 +145,8 @@ def test_attention_fused_and_split(B, T, H, dh, dtype):
     sc3 = ops.attn_scores(q.cuda(), k.cuda(), scale)
     pt3 = ops.softmax_rows(sc3)
     z3 = ops.attn_pv(pt3, v.cuda())
-    assert torch.equal(sc3, sc)
+    # (d_head == 64 runs the mma.sync kernel when fused and the FFMA kernel when split: close, not bit-equal)
+    assert rel_err(sc3.float(), sc.float()) < tol
     assert rel_err(pt3.float(), pt.float()) < tol and rel_err(z3.float(), z.float()) < tol
 
 

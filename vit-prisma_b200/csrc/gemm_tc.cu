@@ -275,6 +275,252 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ 
   }
 }
 
+// =====================================================================================================
+// v2: persistent kernel, one CTA per SM, 128 x BN tiles (BN = 256 for bf16), double-buffered accumulators.
+//
+// Measured on v1 (128x128 tile per CTA, profiles/r01_gemm_notes.md): the mainloop is bound by L2->SM operand
+// bandwidth (a 128x128 tile moves 32 KB per 1 M MACs: 64 flop/B against ~12 TB/s of L2), and the epilogue of a
+// hooked GEMM (two full-size outputs + GELU) costs as much as the mainloop and only overlaps by luck of co-residency.
+// v2 therefore (a) widens the tile to 128x256 (85 flop/B), (b) keeps TWO accumulators in TMEM (2 x BN columns of 512)
+// so that tcgen05.mma fills one while the epilogue drains the other, (c) spreads the epilogue over 8 warps
+// (two per TMEM lane quarter, each owning half of the columns), (d) walks tiles n-fastest so the CTAs of a wave share
+// A rows in L2 while the whole weight matrix stays L2-resident.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <typename T, int NPASS, int BN, int STAGES, int NEPI>
+struct Tc2Cfg {
+  using Base = TcCfg<T, NPASS, BN, STAGES>;
+  static constexpr int THREADS = 64 + NEPI * 32;
+  static constexpr int EPI_STAGE_BYTES = NEPI * 32 * 33 * 4;
+  static constexpr int SMEM_BYTES = Base::RING_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+template <typename T>
+__device__ __forceinline__ void epi_rows_scalar(const EpiParams& ep, const float* stage, int lane, int row0, int nrows, int col) {
+  // one column per lane, rows walked sequentially: every warp store is one contiguous 32-element row segment
+  const T* bias = (const T*)ep.bias;
+  const bool has_bias = bias != nullptr;
+  const float bv = has_bias ? ld_as_float(bias + col) : 0.f;
+  T* o0 = nullptr;
+  if (ep.n_split > 1) {
+    const int blk = col / ep.split_n;
+    o0 = (T*)ep.out_split[blk] + (col - blk * ep.split_n);
+  } else if (ep.out0) {
+    o0 = (T*)ep.out0 + col;
+  }
+  if (o0) o0 += (int64_t)row0 * ep.ld0;
+  T* o1 = ep.out1 ? (T*)ep.out1 + (int64_t)row0 * ep.ld1 + col : nullptr;
+  float* o1lo = ep.out1_lo ? ep.out1_lo + (int64_t)row0 * ep.ld1 + col : nullptr;
+  const T* res = ep.residual ? (const T*)ep.residual + (int64_t)row0 * ep.ldr + col : nullptr;
+  for (int rr = 0; rr < nrows; ++rr) {
+    const float a = stage[rr * 33 + lane];
+    const float v = has_bias ? round_to<T>(round_to<T>(a) + bv) : round_to<T>(a);
+    if (o0) { st_from_float(o0, v); o0 += ep.ld0; }
+    if (o1) {
+      float o;
+      if (res) { o = ld_as_float(res) + v; res += ep.ldr; }
+      else o = apply_act(v, ep.act);
+      st_from_float(o1, o);
+      o1 += ep.ld1;
+      if (o1lo) { *o1lo = o - tf32_trunc(o); o1lo += ep.ld1; }
+    }
+  }
+}
+
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ void ld2(const float* p, float& a, float& b) { float2 t = *reinterpret_cast<const float2*>(p); a = t.x; b = t.y; }
+__device__ __forceinline__ void ld2(const bf16* p, float& a, float& b) {
+  float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+  a = t.x; b = t.y;
+}
+
+template <typename T>
+__device__ __forceinline__ void epi_rows_pair(const EpiParams& ep, const float* stage, int lane, int row0, int nrows, int col0) {
+  // two adjacent columns per lane, two rows per warp instruction (lanes 0-15: even row, 16-31: odd row):
+  // half the load/store instructions of the scalar walk, still whole 32-column row segments per half-warp.
+  const int hi = lane >> 4, cp = lane & 15;
+  const int col = col0 + 2 * cp;
+  if (col >= ep.N) return;   // N % 4 == 0 on this path, so the pair is either fully inside or fully outside
+  const T* bias = (const T*)ep.bias;
+  const bool has_bias = bias != nullptr;
+  float b0 = 0.f, b1 = 0.f;
+  if (has_bias) ld2(bias + col, b0, b1);
+  T* o0 = nullptr;
+  if (ep.n_split > 1) {
+    const int blk = col / ep.split_n;
+    o0 = (T*)ep.out_split[blk] + (col - blk * ep.split_n);
+  } else if (ep.out0) {
+    o0 = (T*)ep.out0 + col;
+  }
+  for (int rr = hi; rr < nrows; rr += 2) {
+    const int64_t row = row0 + rr;
+    float a0 = stage[rr * 33 + 2 * cp], a1 = stage[rr * 33 + 2 * cp + 1];
+    const float v0 = has_bias ? round_to<T>(round_to<T>(a0) + b0) : round_to<T>(a0);
+    const float v1 = has_bias ? round_to<T>(round_to<T>(a1) + b1) : round_to<T>(a1);
+    if (o0) st2(o0 + row * ep.ld0, v0, v1);
+    if (ep.out1) {
+      float x0, x1;
+      if (ep.residual) {
+        ld2((const T*)ep.residual + row * ep.ldr + col, x0, x1);
+        x0 += v0; x1 += v1;
+      } else {
+        x0 = apply_act(v0, ep.act); x1 = apply_act(v1, ep.act);
+      }
+      st2((T*)ep.out1 + row * ep.ld1 + col, x0, x1);
+      if (ep.out1_lo) st2(ep.out1_lo + row * ep.ld1 + col, x0 - tf32_trunc(x0), x1 - tf32_trunc(x1));
+    }
+  }
+}
+
+template <typename T, int NPASS, int BN, int STAGES, int NEPI>
+__global__ void __launch_bounds__(64 + NEPI * 32, 1)
+k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAlo,
+           const __grid_constant__ CUtensorMap tmBlo, int K, EpiParams ep, int num_m_tiles, int num_n_tiles) {
+  using C = TcCfg<T, NPASS, BN, STAGES>;
+  using C2 = Tc2Cfg<T, NPASS, BN, STAGES, NEPI>;
+  constexpr int KIND = sizeof(T) == 2 ? 0 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t ring = (smem0 + 1023u) & ~1023u;
+  const uint32_t epi_stage = ring + C::RING_BYTES;
+  const uint32_t bar_base = epi_stage + C2::EPI_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem0));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (K + C::BK - 1) / C::BK;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (NPASS == 3) { prefetch_tmap(&tmAlo); prefetch_tmap(&tmBlo); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NEPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C2::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n_tiles) * TC_BM, n0 = (tile % num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+          const uint32_t sa = ring + s * C::STAGE_BYTES;
+          const int kc = kb * C::BK;
+          tma_load_2d(sa, &tmA, full_bar(s), kc, m0);
+          if (NPASS == 3) tma_load_2d(sa + C::A_BYTES, &tmAlo, full_bar(s), kc, m0);
+          const uint32_t sb = sa + C::NOP * C::A_BYTES;
+          tma_load_2d(sb, &tmB, full_bar(s), kc, n0);
+          if (NPASS == 3) tma_load_2d(sb + C::B_BYTES, &tmBlo, full_bar(s), kc, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int li = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
+        const int ab = li & 1;
+        const uint32_t aph = (li >> 1) & 1;
+        mbar_wait(tempty_bar(ab), aph ^ 1);      // epilogue has drained this accumulator (first two uses pass at once)
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = ring + s * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::NOP * C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 128 / C::UMMA_K_BYTES; ++k) {
+            const uint32_t koff = k * C::UMMA_K_BYTES;
+            const uint64_t a_hi = make_smem_desc(sa + koff);
+            const uint64_t b_hi = make_smem_desc(sb + koff);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            if (NPASS == 3) {
+              const uint64_t a_lo = make_smem_desc(sa + C::A_BYTES + koff);
+              const uint64_t b_lo = make_smem_desc(sb + C::B_BYTES + koff);
+              tc_mma<KIND>(d_tmem, a_lo, b_hi, C::IDESC, first);
+              tc_mma<KIND>(d_tmem, a_hi, b_lo, C::IDESC, 1u);
+              tc_mma<KIND>(d_tmem, a_hi, b_hi, C::IDESC, 1u);
+            } else {
+              tc_mma<KIND>(d_tmem, a_hi, b_hi, C::IDESC, first);
+            }
+          }
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(tfull_bar(ab));
+      }
+    }
+  } else {
+    const int e = warp - 2;                      // 0 .. NEPI-1
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+    constexpr int CPW = BN / (NEPI / 4);         // columns per epilogue warp
+    const int cbase = (e / 4) * CPW;
+    float* stage = reinterpret_cast<float*>(smem_raw + (epi_stage - smem0)) + e * (32 * 33);
+    int li = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
+      const int m0 = (tile / num_n_tiles) * TC_BM, n0 = (tile % num_n_tiles) * BN;
+      const int ab = li & 1;
+      const uint32_t aph = (li >> 1) & 1;
+      mbar_wait(tfull_bar(ab), aph);
+      tc_fence_after();
+      const int row0 = m0 + quarter * 32;
+      const int nrows = min(32, ep.M - row0);
+#pragma unroll 1
+      for (int c = 0; c < CPW / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + cbase + c * 32), r);
+        tmem_ld_wait();
+        if (c == CPW / 32 - 1) {                 // last read of this accumulator: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(ab));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int col0 = n0 + cbase + c * 32;
+        if (nrows > 0) {
+          if (ep.vec_ok) epi_rows_pair<T>(ep, stage, lane, row0, nrows, col0);
+          else if (col0 + lane < ep.N) epi_rows_scalar<T>(ep, stage, lane, row0, nrows, col0 + lane);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C2::TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -336,6 +582,34 @@ int launch_tc(const PbGemm* g, cudaStream_t st) {
   return PB_OK;
 }
 
+template <typename T, int NPASS, int BN, int STAGES, int NEPI>
+int launch_tc2(const PbGemm* g, cudaStream_t st) {
+  using C2 = Tc2Cfg<T, NPASS, BN, STAGES, NEPI>;
+  CUtensorMap tmA, tmB, tmAlo, tmBlo;
+  PB_TRY(make_map(&tmA, g->A, g->dtype, g->M, g->K, g->lda, TC_BM));
+  PB_TRY(make_map(&tmB, g->B, g->dtype, g->N, g->K, g->ldb, BN));
+  if (NPASS == 3) {
+    PB_TRY(make_map(&tmAlo, g->A_lo, g->dtype, g->M, g->K, g->lda, TC_BM));
+    PB_TRY(make_map(&tmBlo, g->B_lo, g->dtype, g->N, g->K, g->ldb, BN));
+  } else {
+    tmAlo = tmA;
+    tmBlo = tmB;
+  }
+  auto kern = k_gemm_tc2<T, NPASS, BN, STAGES, NEPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
+    attr_done = true;
+  }
+  EpiParams ep = pb_make_epi(g);
+  const int num_m = (g->M + TC_BM - 1) / TC_BM, num_n = (g->N + BN - 1) / BN;
+  int grid = pb_sm_count();
+  if (grid > num_m * num_n) grid = num_m * num_n;
+  kern<<<grid, C2::THREADS, C2::SMEM_BYTES, st>>>(tmA, tmB, tmAlo, tmBlo, g->K, ep, num_m, num_n);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
 }  // namespace
 
 // shape / alignment gate for the tensor-core path
@@ -357,6 +631,13 @@ int pb_gemm_tc(const PbGemm* g, cudaStream_t st) {
                  g->dtype, (long long)g->lda, (long long)g->ldb);
     return PB_EUNSUPPORTED;
   }
-  if (g->dtype == PB_BF16) return launch_tc<bf16, 1, 128, 3>(g, st);
+  static int variant = -1;  // PB_GEMM_TC_VARIANT=1 forces the one-tile-per-CTA kernel (A/B measurements)
+  if (variant < 0) { const char* e = getenv("PB_GEMM_TC_VARIANT"); variant = e ? atoi(e) : 0; }
+  if (g->dtype == PB_BF16) {
+    if (variant != 1 && g->N >= 256) return launch_tc2<bf16, 1, 256, 4, 8>(g, st);
+    if (variant != 1 && g->N >= 128) return launch_tc2<bf16, 1, 128, 4, 4>(g, st);
+    return launch_tc<bf16, 1, 128, 3>(g, st);
+  }
+  if (variant != 1) return launch_tc2<float, 3, 128, 3, 4>(g, st);
   return launch_tc<float, 3, 128, 3>(g, st);
 }
