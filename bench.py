@@ -312,6 +312,164 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ SAE workload (cfg #3: d=768, F=768*32, k=32, 4096 tokens/step, fp32)
+SAE_CFG = dict(d_in=768, expansion=32, k=32, batch=4096)
+
+
+def sae_init_params(d, F, seed=0, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    W_dec = torch.randn(F, d, generator=g)
+    W_dec /= W_dec.norm(dim=1, keepdim=True)
+    W_encT = torch.randn(F, d, generator=g)
+    W_encT /= W_encT.norm(dim=0, keepdim=True) + 1e-12      # reference: rows of W_enc [d,F] unit-norm
+    return dict(W_encT=W_encT.to(device), W_dec=W_dec.to(device), b_enc=torch.zeros(F, device=device), b_dec=torch.zeros(d, device=device))
+
+
+def sae_pool(tokens, d, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    off = torch.randn(d, generator=g)
+    return torch.randn(tokens, d, generator=g) * 2.0 + off
+
+
+def cpu_sae_tokens_per_sec(budget_s=12.0, threads=None, batch=1024):
+    """Oracle port of the reference train_step (dense autograd-equivalent formulas) on host cores, bounded sample."""
+    from oracle.sae_oracle import new_adam_state, sae_train_step
+    threads = threads or _cpu_cores()
+    torch.set_num_threads(threads)
+    d, F, k = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"], SAE_CFG["k"]
+    p0 = sae_init_params(d, F)
+    p = {"W_enc": p0["W_encT"].t().contiguous(), "W_dec": p0["W_dec"], "b_enc": p0["b_enc"], "b_dec": p0["b_dec"]}
+    state = new_adam_state(p)
+    x = sae_pool(batch, d)
+    sae_train_step(p, state, x, k, 1e-3, 1)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        sae_train_step(p, state, x, k, 1e-3, n + 2)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or n >= 16:
+            break
+    return {"value": n * batch / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": f"{n} train steps x {batch} tokens (of the 4096-token step), d=768 F=24576 k=32 fp32, oracle/sae_oracle.py, {dt:.1f}s"}
+
+
+def run_sae(args):
+    world, rank, local = _dist()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from vit_prisma.b200 import _lib as L
+    from vit_prisma.b200.sae_engine import SaeStepEngine, unit_norm_rows_
+    d, F, k, Bt = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"], SAE_CFG["k"], SAE_CFG["batch"]
+    p = sae_init_params(d, F, device=dev)
+    eng = SaeStepEngine(p["W_encT"], p["W_dec"], p["b_enc"], p["b_dec"], k=k)
+    unit_norm_rows_(eng.W_dec)
+    eng.refresh_lo()
+    pool_host = sae_pool(Bt * 16, d, seed=rank).pin_memory()
+    pool = pool_host.to(dev)
+    eng.b_dec.copy_(pool.mean(0))
+    since_fired, act_freq = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
+    lr = 1e-3
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def batch(i):
+        j = (i % 16) * Bt
+        return pool[j:j + Bt]
+
+    for i in range(args.warmup):
+        eng.train_step(batch(i), lr, since_fired, act_freq)
+    barrier()
+    l0 = L.get_lib().pb_launch_count()
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            eng.train_step(batch(i), lr, since_fired, act_freq)
+        e1.record()
+        barrier()
+        dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = L.get_lib().pb_launch_count() - l0
+    # e2e: pinned host tokens -> H2D -> step -> D2H of the step scalars (mse, l0, grad norm, ...)
+    sc_host = torch.empty(8).pin_memory()
+    xin = torch.empty(Bt, d, device=dev)
+    for i in range(2):
+        xin.copy_(pool_host[(i % 16) * Bt:(i % 16 + 1) * Bt], non_blocking=True)
+        sc_host.copy_(eng.train_step(xin, lr, since_fired, act_freq), non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        xin.copy_(pool_host[(i % 16) * Bt:(i % 16 + 1) * Bt], non_blocking=True)
+        sc_host.copy_(eng.train_step(xin, lr, since_fired, act_freq), non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    if rank != 0:
+        return
+    # per-stage device times (one extra instrumented step) -> dominant kernel for the roofline
+    import ctypes as C
+    lib, st = L.get_lib(), torch.cuda.current_stream().cuda_stream
+    stages = {}
+
+    def timed(name, fn, reps=5):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        stages[name] = a.elapsed_time(b) / reps
+
+    x = batch(0).contiguous()
+    timed("encode_topk (prep + encoder GEMM 3xTF32 + topk)", lambda: eng.encode_topk(x))
+    eng.scalars.zero_(); eng.step_count += 1
+    s = eng._desc(x, training=True, lr=lr, since_fired=since_fired, act_freq=act_freq, want_out=False)
+    timed("decode (sparse decode + loss + d_hidden)", lambda: L.check(lib.pb_sae_decode(C.byref(s), st)))
+    timed("backward (csc + per-feature grads + norm)", lambda: (eng.scalars.zero_(), L.check(lib.pb_sae_backward(C.byref(s), st))))
+    timed("adam (clip + projection + Adam + renorm)", lambda: L.check(lib.pb_sae_adam(C.byref(s), st)))
+    peaks = _peaks()
+    tokens = world * Bt * args.steps
+    value = tokens / (dev_ms / 1e3)
+    step_bytes = eng.algorithmic_bytes(Bt)
+    adam_bytes = 60 * d * F            # per matrix element pair: g,p,m,v read (16 B) + p,m,v write (12 B) (x2) + tf32 residual write (4 B)
+    adam_gbs = adam_bytes / (stages["adam (clip + projection + Adam + renorm)"] / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_sae_adam_rows (clip + decoder-parallel-grad removal + Adam + row renorm)", "achieved": adam_gbs,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": adam_gbs / peaks["hbm_gbs"], "traffic": None,
+            "peak_source": peaks["source"] + " copy bandwidth", "algorithmic_bytes_per_launch": adam_bytes,
+            "step_algorithmic_bytes": step_bytes, "step_hbm_gbs": step_bytes / (dev_ms / args.steps / 1e3) / 1e9,
+            "step_hbm_frac": step_bytes / (dev_ms / args.steps / 1e3) / 1e9 / peaks["hbm_gbs"], "stage_ms": stages}
+    cpu = cpu_sae_tokens_per_sec()
+    line = {"metric": "SAE training tokens/sec (TopK SAE, d_model=768, dict=768x32, k=32)", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "sae_topk_train_step", "d_in": d, "d_sae": F, "k": k, "tokens_per_step_per_gpu": Bt,
+                       "encoder_gemm": "tcgen05 3xTF32", "normalize_activations": "layer_norm", "max_grad_norm": 1.0,
+                       "l2": "working set (2 x 75 MB weights + 2 x 150 MB Adam state + 150 MB grads + 403 MB hidden_pre) larger than L2",
+                       "parallelism": f"dp{world}" + (" (independent replicas; P2P all-reduce not wired into bench yet)" if world > 1 else "")},
+            "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * 4, "d2h_bytes_per_step": 32,
+                    "ms_per_step": e2e_ms / args.steps},
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,6 +484,8 @@ def main():
         return run_reference_arm(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    if args.workload == "sae":
+        return run_sae(args)
     run_ours(args)
 
 

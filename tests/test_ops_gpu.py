@@ -133,7 +133,7 @@ def test_attention_fused_and_split(B, T, H, dh, dtype):
     sc_ref = (torch.einsum("bqhe,bkhe->bhqk", q.float(), k.float()) / scale).to(dtype)
     pt_ref = F.softmax(sc_ref.float(), dim=-1).to(dtype)
     z_ref = torch.einsum("bkhe,bhqk->bqhe", v.float(), pt_ref.float()).to(dtype)
-    tol = 3e-6 if dtype == torch.float32 else 1.2e-2
+    tol = 1e-5 if dtype == torch.float32 else 1.2e-2   # fp32: 3xTF32 products (d_head 64) / FFMA, fp32 accumulation
     sc, pt, z = ops.attention(q.cuda(), k.cuda(), v.cuda(), scale)
     assert rel_err(sc.float(), sc_ref.float()) < tol
     assert rel_err(pt.float(), pt_ref.float()) < tol

@@ -18,10 +18,18 @@ TOL = {"fp32": 1e-4, "bf16": 1e-2}
 BF16_ATTN_BAR = 4e-2
 
 
+BF16_BRANCH_BAR = 2e-2    # one bf16 ulp is up to 0.78 % of a value: tensors inside a branch (q/k/v, mlp pre/post, attn_out,
+                          # mlp_out) sit 1-2 ulps apart between two correct implementations; the residual stream does not
+
+
 def _bar(key, dname):
-    if dname == "bf16" and any(s in key for s in ("attn.hook_attn_scores", "attn.hook_pattern", "attn.hook_z")):
+    if dname != "bf16":
+        return TOL[dname]
+    if any(s in key for s in ("attn.hook_attn_scores", "attn.hook_pattern", "attn.hook_z", "hook_attn_out")):
         return BF16_ATTN_BAR
-    return TOL[dname]
+    if any(s in key for s in ("hook_resid", "hook_embed", "hook_full_embed", "hook_ln_pre", "hook_ln_final", "hook_scale", "hook_post_head")):
+        return TOL[dname]
+    return BF16_BRANCH_BAR
 
 
 def _images(batch, cfg, seed=0):

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ 
         T* o0 = nullptr;
         if (ep.n_split > 1) {
           const int blk = col / ep.split_n;
-          o0 = (T*)ep.out_split[blk] + (col - blk * ep.split_n);
+          o0 = (T*)(blk == 0 ? ep.out_split[0] : blk == 1 ? ep.out_split[1] : blk == 2 ? ep.out_split[2] : ep.out_split[3]) + (col - blk * ep.split_n);
         } else if (ep.out0) {
           o0 = (T*)ep.out0 + col;
         }
@@ -309,7 +309,7 @@ __device__ __forceinline__ void epi_rows_scalar(const EpiParams& ep, const float
   T* o0 = nullptr;
   if (ep.n_split > 1) {
     const int blk = col / ep.split_n;
-    o0 = (T*)ep.out_split[blk] + (col - blk * ep.split_n);
+    o0 = (T*)(blk == 0 ? ep.out_split[0] : blk == 1 ? ep.out_split[1] : blk == 2 ? ep.out_split[2] : ep.out_split[3]) + (col - blk * ep.split_n);
   } else if (ep.out0) {
     o0 = (T*)ep.out0 + col;
   }
@@ -340,6 +340,50 @@ __device__ __forceinline__ void ld2(const bf16* p, float& a, float& b) {
   a = t.x; b = t.y;
 }
 
+// GELU(x) = x/2 (1 + erf(x/sqrt2)) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, branch-free, one
+// MUFU.EX2 + one MUFU.RCP): the epilogue of the MLP-in GEMM evaluates it B*T*d_mlp times per block and was issue-bound
+// on libdevice's branchy erff (profiles/r01_gemm_notes.md).  Absolute error of the result <= 0.75e-7 |x|.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, __expf(-ax * ax), 1.f);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
+// out1 flavour of one 32-column chunk, fixed at compile time so the row loop carries no activation switch
+enum { EPI_NONE = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_ACT = 3 };
+
+template <typename T, int MODE, bool HAS_BIAS, bool HAS_OUT0>
+__device__ __forceinline__ void epi_pair_loop(const float* __restrict__ stage, int hi, int cp, int nrows, float b0, float b1, T* o0,
+                                              int64_t ld0, T* o1, float* o1lo, int64_t ld1, const T* res, int64_t ldr, int act) {
+  // rows hi, hi+2, ...: pointers advance by two rows per trip (no per-row multiplies), trips independent -> unrolled for ILP
+  const float* sp = stage + hi * 33 + 2 * cp;
+  if (HAS_OUT0) o0 += hi * ld0;
+  if (MODE != EPI_NONE) { o1 += hi * ld1; if (o1lo) o1lo += hi * ld1; }
+  if (MODE == EPI_RESID) res += hi * ldr;
+#pragma unroll 4
+  for (int rr = hi; rr < nrows; rr += 2) {
+    const float a0 = sp[0], a1 = sp[1];
+    sp += 66;
+    const float v0 = HAS_BIAS ? round_to<T>(round_to<T>(a0) + b0) : round_to<T>(a0);
+    const float v1 = HAS_BIAS ? round_to<T>(round_to<T>(a1) + b1) : round_to<T>(a1);
+    if (HAS_OUT0) { st2(o0, v0, v1); o0 += 2 * ld0; }
+    if (MODE != EPI_NONE) {
+      float x0, x1;
+      if (MODE == EPI_RESID) { ld2(res, x0, x1); x0 += v0; x1 += v1; res += 2 * ldr; }
+      else if (MODE == EPI_GELU) { x0 = gelu_fast(v0); x1 = gelu_fast(v1); }
+      else { x0 = apply_act(v0, act); x1 = apply_act(v1, act); }
+      st2(o1, x0, x1);
+      o1 += 2 * ld1;
+      if (o1lo) { st2(o1lo, x0 - tf32_trunc(x0), x1 - tf32_trunc(x1)); o1lo += 2 * ld1; }
+    }
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void epi_rows_pair(const EpiParams& ep, const float* stage, int lane, int row0, int nrows, int col0) {
   // two adjacent columns per lane, two rows per warp instruction (lanes 0-15: even row, 16-31: odd row):
@@ -348,34 +392,34 @@ __device__ __forceinline__ void epi_rows_pair(const EpiParams& ep, const float* 
   const int col = col0 + 2 * cp;
   if (col >= ep.N) return;   // N % 4 == 0 on this path, so the pair is either fully inside or fully outside
   const T* bias = (const T*)ep.bias;
-  const bool has_bias = bias != nullptr;
   float b0 = 0.f, b1 = 0.f;
-  if (has_bias) ld2(bias + col, b0, b1);
+  if (bias) ld2(bias + col, b0, b1);
   T* o0 = nullptr;
-  if (ep.n_split > 1) {
+  if (ep.n_split > 1) {       // no dynamic indexing of the parameter struct (it would be copied to local memory)
     const int blk = col / ep.split_n;
-    o0 = (T*)ep.out_split[blk] + (col - blk * ep.split_n);
+    void* base = blk == 0 ? ep.out_split[0] : blk == 1 ? ep.out_split[1] : blk == 2 ? ep.out_split[2] : ep.out_split[3];
+    o0 = (T*)base + (col - blk * ep.split_n);
   } else if (ep.out0) {
     o0 = (T*)ep.out0 + col;
   }
-  for (int rr = hi; rr < nrows; rr += 2) {
-    const int64_t row = row0 + rr;
-    float a0 = stage[rr * 33 + 2 * cp], a1 = stage[rr * 33 + 2 * cp + 1];
-    const float v0 = has_bias ? round_to<T>(round_to<T>(a0) + b0) : round_to<T>(a0);
-    const float v1 = has_bias ? round_to<T>(round_to<T>(a1) + b1) : round_to<T>(a1);
-    if (o0) st2(o0 + row * ep.ld0, v0, v1);
-    if (ep.out1) {
-      float x0, x1;
-      if (ep.residual) {
-        ld2((const T*)ep.residual + row * ep.ldr + col, x0, x1);
-        x0 += v0; x1 += v1;
-      } else {
-        x0 = apply_act(v0, ep.act); x1 = apply_act(v1, ep.act);
-      }
-      st2((T*)ep.out1 + row * ep.ld1 + col, x0, x1);
-      if (ep.out1_lo) st2(ep.out1_lo + row * ep.ld1 + col, x0 - tf32_trunc(x0), x1 - tf32_trunc(x1));
-    }
-  }
+  const int64_t ld0 = ep.ld0, ld1 = ep.ld1, ldr = ep.ldr;
+  if (o0) o0 += (int64_t)row0 * ld0;
+  T* o1 = ep.out1 ? (T*)ep.out1 + (int64_t)row0 * ld1 + col : nullptr;
+  float* o1lo = ep.out1_lo ? ep.out1_lo + (int64_t)row0 * ld1 + col : nullptr;
+  const T* res = ep.residual ? (const T*)ep.residual + (int64_t)row0 * ldr + col : nullptr;
+  const int mode = !o1 ? EPI_NONE : res ? EPI_RESID : ep.act == PB_ACT_GELU ? EPI_GELU : EPI_ACT;
+#define PB_EPI(MODE_)                                                                                                             \
+  do {                                                                                                                            \
+    if (bias) { if (o0) epi_pair_loop<T, MODE_, true, true>(stage, hi, cp, nrows, b0, b1, o0, ld0, o1, o1lo, ld1, res, ldr, ep.act); \
+                else epi_pair_loop<T, MODE_, true, false>(stage, hi, cp, nrows, b0, b1, o0, ld0, o1, o1lo, ld1, res, ldr, ep.act); } \
+    else { if (o0) epi_pair_loop<T, MODE_, false, true>(stage, hi, cp, nrows, b0, b1, o0, ld0, o1, o1lo, ld1, res, ldr, ep.act);    \
+           else epi_pair_loop<T, MODE_, false, false>(stage, hi, cp, nrows, b0, b1, o0, ld0, o1, o1lo, ld1, res, ldr, ep.act); }   \
+  } while (0)
+  if (mode == EPI_NONE) PB_EPI(EPI_NONE);
+  else if (mode == EPI_RESID) PB_EPI(EPI_RESID);
+  else if (mode == EPI_GELU) PB_EPI(EPI_GELU);
+  else PB_EPI(EPI_ACT);
+#undef PB_EPI
 }
 
 template <typename T, int NPASS, int BN, int STAGES, int NEPI>
