@@ -226,6 +226,10 @@ typedef struct {
   /* optimizer + bookkeeping state */
   float *m_dec, *v_dec, *m_enc, *v_enc, *m_be, *v_be, *m_bd, *v_bd;
   float* since_fired; float* act_freq;       /* [F] n_forward_passes_since_fired, act_freq_scores (train_sae.py:356-361); may be NULL */
+  /* data parallel (p2p.cu): tokens of the GLOBAL batch (0 = rows) for the 1/(tokens*d) of the mean loss; dist = 1 makes
+   * pb_sae_backward stop after the local gradients (norm / clip / Adam then run in pb_p2p_*), and xsum must already hold the
+   * GLOBAL column sums of x when pb_sae_decode runs (pb_p2p_sum_xsum)                                                     */
+  int32_t global_rows; int32_t dist;
 } PbSaeStep;
 
 /* sae_in = norm_in(x) - b_dec (+ tf32 residual, row mean / std, column sums of x) -- sae.py:78-87, 557-566 */
@@ -250,6 +254,34 @@ PB_API int pb_sae_mse(const float* x, const float* out, float* xsum_scratch, flo
                       pb_stream_t stream);
 /* W[f,:] /= ||W[f,:]|| (set_decoder_norm_to_unit_norm, sae.py:275-277); optional tf32 residual */
 PB_API int pb_unit_norm_rows(float* W, float* W_lo, int32_t F, int32_t d, pb_stream_t stream);
+
+/* ------------------------------------------------ data-parallel SAE step over NVLink peer memory
+ * New functionality (the reference trains on one device): gradients are reduce-scattered by direct peer loads,
+ * the owner of a feature-row slice runs clip + projection + Adam + renorm and stores the new rows into every peer
+ * (all-gather).  No NCCL on this path; torch.distributed is used once, to swap the IPC handles.
+ * Pointer tables are indexed by rank; entry [rank] is the local buffer, the others come from pb_p2p_open.             */
+#define PB_P2P_MAX_RANKS 8
+typedef struct {
+  int32_t rank, world, d, F, step, global_rows;
+  float lr, beta1, beta2, adam_eps, max_grad_norm;
+  float* gW_dec[PB_P2P_MAX_RANKS]; float* gW_encT[PB_P2P_MAX_RANKS]; float* gb_enc[PB_P2P_MAX_RANKS]; float* gb_dec[PB_P2P_MAX_RANKS];
+  float* fired[PB_P2P_MAX_RANKS]; float* xsum[PB_P2P_MAX_RANKS];
+  float* W_dec[PB_P2P_MAX_RANKS]; float* W_encT[PB_P2P_MAX_RANKS]; float* W_encT_lo[PB_P2P_MAX_RANKS]; float* b_enc[PB_P2P_MAX_RANKS];
+  float* norm_parts[PB_P2P_MAX_RANKS]; uint32_t* flags[PB_P2P_MAX_RANKS];
+  /* local only */
+  float *gb_enc_red, *gb_dec_red, *fired_red, *part_accum;     /* [F], [d], [F], [1] */
+  float* b_dec; void* scalars;
+  float *m_dec, *v_dec, *m_enc, *v_enc, *m_be, *v_be, *m_bd, *v_bd;   /* only the owned row slice is touched */
+  float* since_fired; float* act_freq;
+} PbP2PStep;
+PB_API int pb_p2p_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* cudaMalloc (zeroed) + 64-byte IPC handle */
+PB_API int pb_p2p_open(const unsigned char* handle64, void** peer_ptr);
+PB_API int pb_p2p_close(void* peer_ptr);
+PB_API int pb_p2p_free(void* dev_ptr);
+PB_API int pb_p2p_barrier(const PbP2PStep* s, uint32_t epoch, pb_stream_t stream);  /* epoch must increase by 1 per call on every rank */
+PB_API int pb_p2p_sum_xsum(const PbP2PStep* s, float* xsum_global, pb_stream_t stream);
+PB_API int pb_p2p_reduce_scatter(const PbP2PStep* s, pb_stream_t stream);
+PB_API int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -37,8 +37,11 @@ def normalise_in(x: torch.Tensor, mode: str, eps: float = 1e-5):
     return x, torch.zeros_like(x[..., :1]), torch.ones_like(x[..., :1])
 
 
-def sae_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, k: int, mode: str = "layer_norm") -> Dict[str, torch.Tensor]:
-    """p: W_enc [d,F], W_dec [F,d], b_enc [F], b_dec [d]."""
+def sae_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, k: int, mode: str = "layer_norm", xbar: Optional[torch.Tensor] = None,
+                global_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """p: W_enc [d,F], W_dec [F,d], b_enc [F], b_dec [d].
+    ``xbar`` / ``global_rows``: data-parallel shard view -- batch mean and token count of the GLOBAL batch, so that the
+    shard's loss share and gradients sum over shards to the single-process values."""
     xn, mu, std = normalise_in(x, mode)
     sae_in = xn - p["b_dec"]                            # sae.py:564-566
     hidden_pre = sae_in @ p["W_enc"] + p["b_enc"]      # :568-574
@@ -47,16 +50,18 @@ def sae_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, k: int, mode: str =
     feature_acts = torch.zeros_like(hidden_pre).scatter_(-1, top.indices, vals)   # :806-808
     out_n = feature_acts @ p["W_dec"] + p["b_dec"]     # :584-592
     sae_out = out_n * std + mu if mode == "layer_norm" else (out_n * std if mode == "constant_norm_rescale" else out_n)
-    x_centred = x - x.mean(dim=0, keepdim=True)         # :145
+    x_centred = x - (x.mean(dim=0, keepdim=True) if xbar is None else xbar)   # :145
     nf = torch.norm(x_centred, p=2, dim=-1, keepdim=True)
-    mse = (((sae_out - x) ** 2) / nf).mean()            # :146-148
+    mse = (((sae_out - x) ** 2) / nf).sum() / ((global_rows or x.shape[0]) * x.shape[1])   # :146-148 (.mean())
     return dict(sae_in=sae_in, hidden_pre=hidden_pre, idx=top.indices, raw_val=top.values, feature_acts=feature_acts,
                 sae_out=sae_out, mse=mse, nf=nf, std=std, mu=mu)
 
 
-def sae_grads(p: Dict[str, torch.Tensor], x: torch.Tensor, fwd: Dict[str, torch.Tensor], mode: str = "layer_norm") -> Dict[str, torch.Tensor]:
+def sae_grads(p: Dict[str, torch.Tensor], x: torch.Tensor, fwd: Dict[str, torch.Tensor], mode: str = "layer_norm",
+              global_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Gradients of mse wrt the four parameters, closed form (matches loss.backward() of the reference graph)."""
     Bt, d = x.shape
+    Bt = global_rows or Bt
     std = fwd["std"] if mode != "none" else torch.ones_like(fwd["nf"])
     g = 2.0 * (fwd["sae_out"] - x) * std / (fwd["nf"] * Bt * d)          # dL/d out_n
     acts = fwd["feature_acts"]

@@ -173,7 +173,7 @@ def test_product_path_refuses_cpu_tensors():
 
 def test_c_abi_library_exports_every_declared_symbol():
     from vit_prisma.b200 import _lib as L
-    from vit_prisma.b200 import sae_engine  # noqa: F401  (registers the SAE entry points)
+    from vit_prisma.b200 import p2p, sae_engine  # noqa: F401  (register the SAE / P2P entry points)
     header = open(os.path.join(ROOT, "include", "prisma_b200.h")).read()
     declared = set(re.findall(r"PB_API\s+[\w\s\*]+?\b(pb_\w+)\s*\(", header))
     assert len(declared) >= 20
@@ -186,9 +186,13 @@ def test_c_abi_library_exports_every_declared_symbol():
 
 def test_c_abi_struct_layouts_match_the_compiled_library():
     from vit_prisma.b200 import _lib as L
-    from vit_prisma.b200 import sae_engine  # noqa: F401  (appends PbSaeStep to ABI_STRUCTS)
+    from vit_prisma.b200 import p2p, sae_engine  # noqa: F401  (append PbSaeStep / PbP2PStep to ABI_STRUCTS)
     lib = ctypes.CDLL(str(L.LIB_PATH))
     lib.pb_abi_sizeof.restype = ctypes.c_int
+    assert len(L.ABI_STRUCTS) == 9
     for idx, struct in enumerate(L.ABI_STRUCTS):
+        if struct is None:      # device-side only struct
+            assert lib.pb_abi_sizeof(idx) > 0
+            continue
         assert lib.pb_abi_sizeof(idx) == ctypes.sizeof(struct), struct.__name__
     assert lib.pb_abi_sizeof(10_000) == -1

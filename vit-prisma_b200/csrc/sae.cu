@@ -383,15 +383,15 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
     // sort the (short) entry list by flat index == by token: insertion sort by lane 0 for tiny lists,
     // odd-even transposition across lanes would be overkill here
     const int len = e1 - e0;
-    if (len > 1 && len <= 64) {
-      if (lane == 0) {
-        for (int i = e0 + 1; i < e1; ++i) {
-          const int key = entries[i];
-          int j = i - 1;
-          while (j >= e0 && entries[j] > key) { entries[j + 1] = entries[j]; --j; }
-          entries[j + 1] = key;
-        }
-      }
+    if (len > 1 && len <= 32) {
+      // rank-by-counting in registers: lane i holds entry i, its sorted slot = number of smaller entries (entries are distinct).
+      // (A serial insertion sort through global memory here cost 3.6 ms per step: profiles/r01_sae_notes.md.)
+      const int mine = lane < len ? entries[e0 + lane] : 0x7fffffff;
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rank += __shfl_sync(0xffffffffu, mine, j) < mine ? 1 : 0;
+      __syncwarp();
+      if (lane < len) entries[e0 + rank] = mine;
       __syncwarp();
     }
     float ad[CHUNKS][4], ae[CHUNKS][4];
@@ -452,6 +452,11 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
   }
   for (int c = threadIdx.x; c < d; c += blockDim.x)
     if (sm_bd[c] != 0.f) atomicAdd(gbdec2 + c, sm_bd[c]);
+}
+
+__global__ void k_sae_gbdec(const float* __restrict__ gcol, const float* __restrict__ gbdec2, float* __restrict__ gb_dec, int d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < d) gb_dec[c] = gcol[c] - gbdec2[c];
 }
 
 // 6. finalize: gb_dec = colsum(g) - gbdec2 ; total norm ; clip coefficient (train_sae.py:394-397)
@@ -748,7 +753,7 @@ extern "C" int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream) {
   const int d = s->d, ch = chunks_for(d);
   PB_DISPATCH_CHUNKS(ch, (k_sae_decode<C_><<<(s->rows + 7) / 8, 256, 0, st>>>(
       s->x, s->xsum, s->mu, s->sd, s->idx, s->val, s->W_dec, s->b_dec, s->sae_out, s->g, s->dval, (SaeScalars*)s->scalars, s->rows, d, s->k,
-      s->norm_mode, s->training, 1.f / (float)s->rows)));
+      s->norm_mode, s->training, 1.f / (float)(s->global_rows > 0 ? s->global_rows : s->rows))));
   PB_LAUNCH_CHECK();
   if (!s->training) {  // inference: publish mse / l0 now (the training path does it in k_sae_finalize)
     k_sae_fwd_scalars<<<1, 1, 0, st>>>((SaeScalars*)s->scalars, 1.f / ((float)s->rows * (float)d), 1.f / (float)s->rows);
@@ -779,6 +784,11 @@ extern "C" int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream) {
                                                                                 s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc, s->gbdec2,
                                                                                 s->fired, (SaeScalars*)s->scalars, F, d, s->k)));
   PB_LAUNCH_CHECK();
+  if (s->dist) {  // data parallel: only the local gb_dec; norm / clip happen after the peer reduction (p2p.cu)
+    k_sae_gbdec<<<(d + 255) / 256, 256, 0, st>>>(s->gcol, s->gbdec2, s->gb_dec, d);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+  }
   k_sae_finalize<<<1, 256, 0, st>>>(s->gcol, s->gbdec2, s->gb_dec, (SaeScalars*)s->scalars, d, s->max_grad_norm,
                                     1.f / ((float)s->rows * (float)d), 1.f / (float)s->rows);
   PB_LAUNCH_CHECK();
@@ -853,8 +863,9 @@ extern "C" int pb_sae_mse(const float* x, const float* out, float* xsum_scratch,
   return PB_OK;
 }
 
+int pb_abi_sizeof_p2p(int which);  // p2p.cu
 int pb_abi_sizeof_sae(int which) {
   if (which == 6) return (int)sizeof(PbSaeStep);
   if (which == 7) return (int)sizeof(SaeScalars);
-  return -1;
+  return pb_abi_sizeof_p2p(which);
 }

@@ -1,0 +1,190 @@
+"""Data-parallel SAE training over NVLink peer memory (csrc/p2p.cu) -- host side.
+
+``P2PGroup`` allocates peer-visible buffers through the library (cudaMalloc + CUDA IPC handle), swaps the 64-byte
+handles between the ranks ONCE (``torch.distributed.all_gather_object`` -- plumbing, not the data path) and opens every
+peer's buffers.  ``SaeDPEngine`` is ``SaeStepEngine`` with its parameters, gradients and a few small vectors living in
+those buffers and the optimizer step replaced by reduce-scatter (peer loads) -> clip/project/Adam on the owned row
+slice -> all-gather (peer stores).  Single-GPU semantics are preserved: the loss is the mean over the GLOBAL batch
+(column mean of x, 1/(tokens*d) factor), the clip norm is that of the summed gradient, dead-feature counters are summed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from .ops import _stream
+from .sae_engine import PbSaeStep, SaeStepEngine
+
+vp, i32, i64, f32, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32
+MAX_RANKS = 8
+_TABLES = ("gW_dec", "gW_encT", "gb_enc", "gb_dec", "fired", "xsum", "W_dec", "W_encT", "W_encT_lo", "b_enc", "norm_parts", "flags")
+
+
+class PbP2PStep(C.Structure):
+    _fields_ = (
+        [(n, i32) for n in ("rank", "world", "d", "F", "step", "global_rows")]
+        + [(n, f32) for n in ("lr", "beta1", "beta2", "adam_eps", "max_grad_norm")]
+        + [(n, vp * MAX_RANKS) for n in _TABLES]
+        + [(n, vp) for n in ("gb_enc_red", "gb_dec_red", "fired_red", "part_accum", "b_dec", "scalars",
+                             "m_dec", "v_dec", "m_enc", "v_enc", "m_be", "v_be", "m_bd", "v_bd", "since_fired", "act_freq")]
+    )
+
+
+L.ABI_STRUCTS.extend([None, PbP2PStep])      # index 7 is the device-side scalars struct (no ctypes twin), 8 = PbP2PStep
+L.register_signatures({
+    "pb_p2p_alloc": (i32, [i64, C.POINTER(vp), C.c_char_p]),
+    "pb_p2p_open": (i32, [C.c_char_p, C.POINTER(vp)]),
+    "pb_p2p_close": (i32, [vp]),
+    "pb_p2p_free": (i32, [vp]),
+    "pb_p2p_barrier": (i32, [C.POINTER(PbP2PStep), u32, vp]),
+    "pb_p2p_sum_xsum": (i32, [C.POINTER(PbP2PStep), vp, vp]),
+    "pb_p2p_reduce_scatter": (i32, [C.POINTER(PbP2PStep), vp]),
+    "pb_p2p_adam_allgather": (i32, [C.POINTER(PbP2PStep), vp]),
+})
+
+
+def shard_bounds(F: int, rank: int, world: int):
+    """Feature rows owned by ``rank``: contiguous, equal slices (F must divide evenly -- d_sae is d_in * expansion)."""
+    if F % world:
+        raise ValueError(f"d_sae={F} is not divisible by world size {world}")
+    per = F // world
+    return rank * per, (rank + 1) * per
+
+
+class _RawCuda:
+    """Minimal ``__cuda_array_interface__`` carrier so torch can view library-owned device memory without copying."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+
+
+_TYPESTR = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}
+
+
+class P2PGroup:
+    def __init__(self, rank: int, world: int, device: torch.device, exchange: Optional[Callable[[dict], List[dict]]] = None):
+        if not 1 <= world <= MAX_RANKS:
+            raise ValueError(f"world size {world} outside 1..{MAX_RANKS}")
+        self.rank, self.world, self.device = rank, world, device
+        self._exchange = exchange or self._exchange_dist
+        self.local: Dict[str, torch.Tensor] = {}
+        self._ptr: Dict[str, int] = {}
+        self._handle: Dict[str, bytes] = {}
+        self.peer_ptr: Dict[str, List[int]] = {}
+        self.epoch = 0
+
+    @staticmethod
+    def _exchange_dist(mine: dict) -> List[dict]:
+        import torch.distributed as dist
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, mine)
+        return out
+
+    def alloc(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = max(n, 1) * torch.empty((), dtype=dtype).element_size()
+        ptr = vp()
+        handle = C.create_string_buffer(64)
+        L.check(L.get_lib().pb_p2p_alloc(nbytes, C.byref(ptr), handle), "pb_p2p_alloc")
+        t = torch.as_tensor(_RawCuda(ptr.value, shape, _TYPESTR[dtype]), device=self.device)
+        self.local[name], self._ptr[name], self._handle[name] = t, ptr.value, handle.raw
+        return t
+
+    def connect(self) -> None:
+        """Swap IPC handles and open every peer's buffers (collective: call on all ranks after all ``alloc`` calls)."""
+        everyone = self._exchange(dict(self._handle))
+        for name in self._handle:
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(self._ptr[name])
+                    continue
+                peer = vp()
+                L.check(L.get_lib().pb_p2p_open(everyone[r][name], C.byref(peer)), f"pb_p2p_open({name}, rank {r})")
+                ptrs.append(peer.value)
+            self.peer_ptr[name] = ptrs
+
+    def fill_tables(self, s: PbP2PStep) -> None:
+        s.rank, s.world = self.rank, self.world
+        for name in _TABLES:
+            arr = getattr(s, name)
+            for r, p in enumerate(self.peer_ptr[name]):
+                arr[r] = p
+
+    def barrier(self, s: PbP2PStep) -> None:
+        self.epoch += 1
+        L.check(L.get_lib().pb_p2p_barrier(C.byref(s), self.epoch, _stream()), "pb_p2p_barrier")
+
+
+class SaeDPEngine(SaeStepEngine):
+    """``SaeStepEngine`` whose optimizer step is the NVLink reduce-scatter / sharded Adam / all-gather of csrc/p2p.cu."""
+
+    def __init__(self, group: P2PGroup, W_encT: torch.Tensor, W_dec: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, k: int, **kw):
+        self.group = group
+        F, d = W_dec.shape
+        shard_bounds(F, group.rank, group.world)
+        g = group
+        shared = {"W_encT": g.alloc("W_encT", (F, d)), "W_dec": g.alloc("W_dec", (F, d)), "b_enc": g.alloc("b_enc", (F,))}
+        shared["W_encT"].copy_(W_encT)
+        shared["W_dec"].copy_(W_dec)
+        shared["b_enc"].copy_(b_enc)
+        self._shared_lo = g.alloc("W_encT_lo", (F, d))
+        for name, shape in (("gW_dec", (F, d)), ("gW_encT", (F, d)), ("gb_enc", (F,)), ("gb_dec", (d,)), ("fired", (F,)), ("xsum", (d,)),
+                            ("norm_parts", (MAX_RANKS,))):
+            g.alloc(name, shape)
+        g.alloc("flags", (MAX_RANKS,), dtype=torch.int32)
+        super().__init__(shared["W_encT"], shared["W_dec"], shared["b_enc"], b_dec.clone().contiguous(), k, **kw)
+        # re-point the buffers peers must reach at the shared allocations
+        self.W_encT_lo = self._shared_lo
+        self.refresh_lo()
+        self.gW_dec, self.gW_encT, self.gb_enc, self.gb_dec = g.local["gW_dec"], g.local["gW_encT"], g.local["gb_enc"], g.local["gb_dec"]
+        self.fired = g.local["fired"]
+        self.xsum_local = g.local["xsum"]
+        dev = W_dec.device
+        self.gb_enc_red, self.gb_dec_red, self.fired_red = torch.zeros(F, device=dev), torch.zeros(d, device=dev), torch.zeros(F, device=dev)
+        self.part_accum = torch.zeros(1, device=dev)
+        g.connect()
+        torch.cuda.synchronize()
+
+    def _p2p_desc(self, rows: int, lr: float, since_fired, act_freq) -> PbP2PStep:
+        s = PbP2PStep()
+        self.group.fill_tables(s)
+        s.d, s.F, s.step, s.global_rows = self.d, self.F, self.step_count, rows * self.group.world
+        s.lr, s.beta1, s.beta2, s.adam_eps, s.max_grad_norm = lr, self.betas[0], self.betas[1], self.adam_eps, self.max_grad_norm
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        s.gb_enc_red, s.gb_dec_red, s.fired_red, s.part_accum = p(self.gb_enc_red), p(self.gb_dec_red), p(self.fired_red), p(self.part_accum)
+        s.b_dec, s.scalars = p(self.b_dec), p(self.scalars)
+        s.m_dec, s.v_dec, s.m_enc, s.v_enc = p(self.m_dec), p(self.v_dec), p(self.m_enc), p(self.v_enc)
+        s.m_be, s.v_be, s.m_bd, s.v_bd = p(self.m_be), p(self.v_be), p(self.m_bd), p(self.v_bd)
+        s.since_fired, s.act_freq = p(since_fired), p(act_freq)
+        return s
+
+    @torch.no_grad()
+    def train_step(self, x: torch.Tensor, lr: float, since_fired=None, act_freq=None, want_out: bool = False) -> torch.Tensor:
+        lib, st, g = L.get_lib(), _stream(), self.group
+        x = x.contiguous().float()
+        rows = x.shape[0]
+        # prep writes THIS rank's column sums of x into the shared xsum; decode needs the GLOBAL sums
+        xsum_global, self.xsum = self.xsum, self.xsum_local
+        self.encode_topk(x)
+        self.xsum = xsum_global
+        self.scalars.zero_()
+        self.step_count += 1
+        ps = self._p2p_desc(rows, float(lr), since_fired, act_freq)
+        g.barrier(ps)
+        L.check(lib.pb_p2p_sum_xsum(C.byref(ps), self.xsum.data_ptr(), st), "pb_p2p_sum_xsum")
+        s = self._desc(x, training=True, lr=float(lr), since_fired=since_fired, act_freq=act_freq, want_out=want_out)
+        s.global_rows, s.dist = rows * g.world, 1
+        L.check(lib.pb_sae_decode(C.byref(s), st), "pb_sae_decode")
+        L.check(lib.pb_sae_backward(C.byref(s), st), "pb_sae_backward")
+        g.barrier(ps)                                   # every rank's local gradients are complete
+        L.check(lib.pb_p2p_reduce_scatter(C.byref(ps), st), "pb_p2p_reduce_scatter")
+        g.barrier(ps)                                   # norm partials published; all peer reads of this step are done
+        L.check(lib.pb_p2p_adam_allgather(C.byref(ps), st), "pb_p2p_adam_allgather")
+        g.barrier(ps)                                   # every rank holds the updated parameters
+        return self.scalars

@@ -34,6 +34,7 @@ class PbSaeStep(C.Structure):
             "csc_off", "csc_cursor", "csc_entries", "gW_dec", "gW_encT", "gb_enc", "gb_dec", "gcol", "gbdec2",
             "fired", "scalars", "m_dec", "v_dec", "m_enc", "v_enc", "m_be", "v_be", "m_bd", "v_bd",
             "since_fired", "act_freq")]
+        + [("global_rows", i32), ("dist", i32)]
     )
 
 
