@@ -364,12 +364,16 @@ def run_sae(args):
     from vit_prisma.b200.sae_engine import SaeStepEngine, unit_norm_rows_
     d, F, k, Bt = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"], SAE_CFG["k"], SAE_CFG["batch"]
     p = sae_init_params(d, F, device=dev)
-    eng = SaeStepEngine(p["W_encT"], p["W_dec"], p["b_enc"], p["b_dec"], k=k)
+    if world > 1:      # data parallel over NVLink peer memory: Bt tokens per GPU, one global step (csrc/p2p.cu)
+        from vit_prisma.b200.p2p import P2PGroup, SaeDPEngine
+        eng = SaeDPEngine(P2PGroup(rank, world, dev), p["W_encT"], p["W_dec"], p["b_enc"], p["b_dec"], k=k)
+    else:
+        eng = SaeStepEngine(p["W_encT"], p["W_dec"], p["b_enc"], p["b_dec"], k=k)
     unit_norm_rows_(eng.W_dec)
     eng.refresh_lo()
     pool_host = sae_pool(Bt * 16, d, seed=rank).pin_memory()
     pool = pool_host.to(dev)
-    eng.b_dec.copy_(pool.mean(0))
+    eng.b_dec.copy_(sae_pool(Bt * 16, d, seed=0).mean(0).to(dev))     # identical b_dec init on every rank
     since_fired, act_freq = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
     lr = 1e-3
 
@@ -462,7 +466,8 @@ def run_sae(args):
             "config": {"workload": "sae_topk_train_step", "d_in": d, "d_sae": F, "k": k, "tokens_per_step_per_gpu": Bt,
                        "encoder_gemm": "tcgen05 3xTF32", "normalize_activations": "layer_norm", "max_grad_norm": 1.0,
                        "l2": "working set (2 x 75 MB weights + 2 x 150 MB Adam state + 150 MB grads + 403 MB hidden_pre) larger than L2",
-                       "parallelism": f"dp{world}" + (" (independent replicas; P2P all-reduce not wired into bench yet)" if world > 1 else "")},
+                       "parallelism": f"dp{world}" + (" (NVLink peer-memory reduce-scatter + sharded Adam + all-gather, no NCCL on the data path; "
+                                                       f"{int((world - 1) / world * (2 * d * F * 4 * 2 + d * F * 4) / 1e6)} MB over NVLink per GPU per step)" if world > 1 else "")},
             "clocks": clocks.summary(), "gpu_launches": int(launches),
             "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * 4, "d2h_bytes_per_step": 32,
                     "ms_per_step": e2e_ms / args.steps},

@@ -682,6 +682,7 @@ int pb_gemm_tc(const PbGemm* g, cudaStream_t st) {
     if (variant != 1 && g->N >= 128) return launch_tc2<bf16, 1, 128, 4, 4>(g, st);
     return launch_tc<bf16, 1, 128, 3>(g, st);
   }
+  if (variant == 2 && g->N >= 256) return launch_tc2<float, 3, 256, 2, 8>(g, st);   // wider tile, shallower ring (A/B)
   if (variant != 1) return launch_tc2<float, 3, 128, 3, 4>(g, st);
   return launch_tc<float, 3, 128, 3>(g, st);
 }
