@@ -230,6 +230,9 @@ typedef struct {
    * pb_sae_backward stop after the local gradients (norm / clip / Adam then run in pb_p2p_*), and xsum must already hold the
    * GLOBAL column sums of x when pb_sae_decode runs (pb_p2p_sum_xsum)                                                     */
   int32_t global_rows; int32_t dist;
+  /* scratch of pb_sae_backward for features selected by more than 64 tokens (their lists are split across warps):
+   * work_bytes >= 8 + 4*F + 8*(rows*k/32 + F + 1)                                                                        */
+  void* work; int64_t work_bytes;
 } PbSaeStep;
 
 /* sae_in = norm_in(x) - b_dec (+ tf32 residual, row mean / std, column sums of x) -- sae.py:78-87, 557-566 */

@@ -120,6 +120,42 @@ def test_engine_forward_matches_oracle_midsize():
         assert abs(eng.scalars_dict()["mse"] - ref["mse"].item()) <= 1e-4 * ref["mse"].item()
 
 
+def test_hot_features_split_lists_match_oracle_gradients():
+    """A decoder bias far from the data makes a few features win TopK on (almost) every token -- the regime of real
+    activations.  Their per-feature lists (hundreds of tokens) take the split-across-warps path of pb_sae_backward."""
+    L = _L()
+    from oracle.sae_oracle import sae_grads
+    from vit_prisma.b200.sae_engine import SaeStepEngine
+    import ctypes as C
+    d, F, k, rows = 64, 1024, 16, 768
+    g = torch.Generator().manual_seed(11)
+    p = {"W_enc": torch.randn(d, F, generator=g) / math.sqrt(d), "W_dec": torch.randn(F, d, generator=g), "b_enc": torch.zeros(F),
+         "b_dec": 3.0 * torch.randn(d, generator=g)}
+    p["W_dec"] /= p["W_dec"].norm(dim=1, keepdim=True)
+    x = torch.randn(rows, d, generator=g) * 2.0 + torch.randn(d, generator=g)
+    fwd = sae_forward(p, x, k)
+    counts = torch.bincount(fwd["idx"].reshape(-1), minlength=F)
+    assert int(counts.max()) > 256, "test premise: at least one hot feature"
+    ref = sae_grads(p, x, fwd)
+    eng = SaeStepEngine(p["W_enc"].t().contiguous().cuda(), p["W_dec"].clone().cuda(), p["b_enc"].clone().cuda(), p["b_dec"].clone().cuda(), k=k,
+                        gemm_impl=L.GEMM_SIMT)
+    xs = x.cuda()
+    eng.encode_topk(xs)
+    eng.scalars.zero_()
+    eng.step_count = 1
+    s = eng._desc(xs, training=True, lr=1e-3)
+    L.check(L.get_lib().pb_sae_decode(C.byref(s), torch.cuda.current_stream().cuda_stream))
+    L.check(L.get_lib().pb_sae_backward(C.byref(s), torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(eng.idx.cpu().long(), fwd["idx"])
+    assert_close(eng.gW_dec.cpu(), ref["W_dec"], 1e-4, "dL/dW_dec")
+    assert_close(eng.gW_encT.t().cpu(), ref["W_enc"], 1e-4, "dL/dW_enc")
+    assert_close(eng.gb_enc.cpu(), ref["b_enc"], 1e-4, "dL/db_enc")
+    assert_close(eng.gb_dec.cpu(), ref["b_dec"], 1e-4, "dL/db_dec")
+    assert torch.equal(eng.fired.cpu(), (fwd["feature_acts"] > 0).float().sum(0))
+    norm_ref = math.sqrt(sum((v.double() ** 2).sum().item() for v in ref.values()))
+    assert abs(eng.scalars_dict()["grad_norm"] - norm_ref) <= 1e-4 * norm_ref
+
+
 # ---------------------------------------------------------------------------- module / trainer surface
 def _cfg(**kw):
     from vit_prisma.sae.config import VisionModelSAERunnerConfig

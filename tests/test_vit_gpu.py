@@ -147,4 +147,5 @@ def test_clip_b32_bf16_matches_oracle():
             ref_vs_truth = max(ref_vs_truth, rel_err(ref.float(), cache_true[k]))
     print(f"[bf16] worst key {worst[0]} rel err {worst[1]:.2e}; residual stream vs fp32 truth: ours {ours_vs_truth:.2e}, reference-bf16 {ref_vs_truth:.2e}")
     assert ours_vs_truth <= 1.25 * ref_vs_truth + 1e-3, "less accurate than the reference's own bf16 path"
-    assert rel_err(out.cpu(), out_ref) <= 1e-2
+    assert rel_err(out.cpu(), out_ref) <= 2e-2            # same two-ulp budget as the residual stream it is computed from
+    assert rel_err(out.cpu().float(), out_true) <= 1.25 * rel_err(out_ref.float(), out_true) + 2e-3

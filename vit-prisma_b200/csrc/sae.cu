@@ -366,12 +366,17 @@ __global__ void __launch_bounds__(256) k_csc_fill(const int* __restrict__ idx, i
 //    fired[f]   = number of tokens with relu(val) > 0 ; gnorm_sq += all squares
 // Entry order inside a feature list comes from atomics, so the fp32 sums are order-nondeterministic at the
 // 1e-7 level; the list is therefore sorted by token index first (lists are short: mean Bt*k/F).
+constexpr int SAE_LONG_LIST = 64;    // lists longer than this are split across warps
+constexpr int SAE_LONG_CHUNK = 32;   // entries per work item of the long-list kernel
+struct SaeWorkHeader { int n_chunks, n_long; };   // followed in memory by work_feats[F] and work_chunks[2 * capacity]
+
 template <int CHUNKS>
 __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, int* __restrict__ entries, const float* __restrict__ val,
                                                    const float* __restrict__ dval, const float* __restrict__ g, const float* __restrict__ sae_in,
                                                    const float* __restrict__ W_encT, float* __restrict__ gW_dec, float* __restrict__ gW_encT,
                                                    float* __restrict__ gb_enc, float* __restrict__ gbdec2, float* __restrict__ fired,
-                                                   SaeScalars* __restrict__ sc, int F, int d, int k) {
+                                                   SaeScalars* __restrict__ sc, int F, int d, int k, SaeWorkHeader* __restrict__ work,
+                                                   int* __restrict__ work_feats, int* __restrict__ work_chunks) {
   extern __shared__ __align__(16) float sm_bd[];  // [d] per-CTA partial of gbdec2
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nvec = d >> 2;
@@ -380,9 +385,36 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
   float nsq = 0.f;
   for (int f = blockIdx.x * nw + warp; f < F; f += gridDim.x * nw) {
     const int e0 = off[f], e1 = off[f + 1];
-    // sort the (short) entry list by flat index == by token: insertion sort by lane 0 for tiny lists,
-    // odd-even transposition across lanes would be overkill here
     const int len = e1 - e0;
+    if (len > SAE_LONG_LIST) {
+      // hot feature (selected by many tokens -- with real activations a handful of features fire on almost every token):
+      // one warp walking thousands of entries would be the tail of the whole step (measured 2.4 ms).  Zero its rows, queue
+      // its list in chunks of SAE_LONG_CHUNK entries for k_sae_grads_long, count its norm in k_sae_norm_long.
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c4 = i * 32 + lane;
+        if (c4 < nvec) {
+          const float z4[4] = {0.f, 0.f, 0.f, 0.f};
+          st4(gW_dec + (int64_t)f * d + 4 * c4, z4);
+          st4(gW_encT + (int64_t)f * d + 4 * c4, z4);
+        }
+      }
+      const int nchunks = (len + SAE_LONG_CHUNK - 1) / SAE_LONG_CHUNK;
+      int base = 0, lslot = 0;
+      if (lane == 0) {
+        gb_enc[f] = 0.f;
+        fired[f] = 0.f;
+        base = atomicAdd(&work->n_chunks, nchunks);
+        lslot = atomicAdd(&work->n_long, 1);
+        work_feats[lslot] = f;
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int c = lane; c < nchunks; c += 32) {
+        work_chunks[2 * (base + c)] = f;
+        work_chunks[2 * (base + c) + 1] = e0 + c * SAE_LONG_CHUNK;
+      }
+      continue;
+    }
     if (len > 1 && len <= 32) {
       // rank-by-counting in registers: lane i holds entry i, its sorted slot = number of smaller entries (entries are distinct).
       // (A serial insertion sort through global memory here cost 3.6 ms per step: profiles/r01_sae_notes.md.)
@@ -452,6 +484,92 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
   }
   for (int c = threadIdx.x; c < d; c += blockDim.x)
     if (sm_bd[c] != 0.f) atomicAdd(gbdec2 + c, sm_bd[c]);
+}
+
+// 5b. hot features: one warp per chunk of SAE_LONG_CHUNK list entries, partial rows added with 16-byte red.global.add
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) k_sae_grads_long(const int* __restrict__ off, const int* __restrict__ entries, const float* __restrict__ val,
+                                                        const float* __restrict__ dval, const float* __restrict__ g,
+                                                        const float* __restrict__ sae_in, const float* __restrict__ W_encT,
+                                                        float* __restrict__ gW_dec, float* __restrict__ gW_encT, float* __restrict__ gb_enc,
+                                                        float* __restrict__ gbdec2, float* __restrict__ fired, int d, int k,
+                                                        const SaeWorkHeader* __restrict__ work, const int* __restrict__ work_chunks) {
+  extern __shared__ __align__(16) float sm_bd[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nvec = d >> 2;
+  const int n_items = work->n_chunks;
+  if (n_items == 0) return;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) sm_bd[c] = 0.f;
+  __syncthreads();
+  for (int item = blockIdx.x * nw + warp; item < n_items; item += gridDim.x * nw) {
+    const int f = work_chunks[2 * item], p0 = work_chunks[2 * item + 1];
+    const int p1 = min(off[f + 1], p0 + SAE_LONG_CHUNK);
+    float ad[CHUNKS][4], ae[CHUNKS][4];
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) ad[i][0] = ad[i][1] = ad[i][2] = ad[i][3] = ae[i][0] = ae[i][1] = ae[i][2] = ae[i][3] = 0.f;
+    float gbe = 0.f, npos = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const int e = entries[p];
+      const int b = e / k;
+      const float a = fmaxf(val[e], 0.f);
+      const float dp = dval[e];
+      if (a > 0.f) npos += 1.f;
+      gbe += dp;
+      const float* gr = g + (int64_t)b * d;
+      const float* sr = sae_in + (int64_t)b * d;
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c4 = i * 32 + lane;
+        if (c4 < nvec) {
+          float gv[4], sv[4];
+          ld4(gr + 4 * c4, gv);
+          ld4(sr + 4 * c4, sv);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { ad[i][q] = fmaf(a, gv[q], ad[i][q]); ae[i][q] = fmaf(dp, sv[q], ae[i][q]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nvec) {
+        atomicAdd(reinterpret_cast<float4*>(gW_dec + (int64_t)f * d + 4 * c4), make_float4(ad[i][0], ad[i][1], ad[i][2], ad[i][3]));
+        atomicAdd(reinterpret_cast<float4*>(gW_encT + (int64_t)f * d + 4 * c4), make_float4(ae[i][0], ae[i][1], ae[i][2], ae[i][3]));
+        if (gbe != 0.f) {
+          float w[4];
+          ld4(W_encT + (int64_t)f * d + 4 * c4, w);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) atomicAdd(&sm_bd[4 * c4 + q], gbe * w[q]);
+        }
+      }
+    }
+    if (lane == 0) {
+      atomicAdd(gb_enc + f, gbe);
+      atomicAdd(fired + f, npos);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    if (sm_bd[c] != 0.f) atomicAdd(gbdec2 + c, sm_bd[c]);
+}
+
+// 5c. squared norm of the completed hot-feature rows (not additive over chunks, so it waits for 5b)
+__global__ void __launch_bounds__(256) k_sae_norm_long(const float* __restrict__ gW_dec, const float* __restrict__ gW_encT,
+                                                       const float* __restrict__ gb_enc, SaeScalars* __restrict__ sc, int d,
+                                                       const SaeWorkHeader* __restrict__ work, const int* __restrict__ work_feats) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int n = work->n_long;
+  float nsq = 0.f;
+  for (int li = blockIdx.x * nw + warp; li < n; li += gridDim.x * nw) {
+    const int f = work_feats[li];
+    for (int c = lane; c < d; c += 32) {
+      const float a = gW_dec[(int64_t)f * d + c], b = gW_encT[(int64_t)f * d + c];
+      nsq += a * a + b * b;
+    }
+    if (lane == 0) nsq += gb_enc[f] * gb_enc[f];
+  }
+  nsq = warp_sum(nsq);
+  if (lane == 0 && nsq != 0.f) atomicAdd(&sc->gnorm_sq, nsq);
 }
 
 __global__ void k_sae_gbdec(const float* __restrict__ gcol, const float* __restrict__ gbdec2, float* __restrict__ gb_dec, int d) {
@@ -779,11 +897,29 @@ extern "C" int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream) {
   const int rpc = 32;
   k_colsum<<<(s->rows + rpc - 1) / rpc, 256, 0, st>>>(s->g, s->gcol, s->rows, d, rpc);
   PB_LAUNCH_CHECK();
+  // work area for hot features: header | work_feats[F] | work_chunks[2 * (rows*k / CHUNK + F + 1)]
+  const int64_t cap = n / SAE_LONG_CHUNK + F + 1;
+  const int64_t need = (int64_t)sizeof(SaeWorkHeader) + 4 * (int64_t)F + 8 * cap;
+  PB_CHECK_ARG(s->work && s->work_bytes >= need, "pb_sae_backward: work buffer too small (%lld < %lld bytes)", (long long)s->work_bytes,
+               (long long)need);
+  SaeWorkHeader* wh = (SaeWorkHeader*)s->work;
+  int* work_feats = (int*)(wh + 1);
+  int* work_chunks = work_feats + F;
+  PB_CUDA(cudaMemsetAsync(wh, 0, sizeof(SaeWorkHeader), st));
   const int grid = persistent_grid(8, F);
   PB_DISPATCH_CHUNKS(ch, (k_sae_grads<C_><<<grid, 256, sizeof(float) * d, st>>>(s->csc_off, s->csc_entries, s->val, s->dval, s->g, s->sae_in,
                                                                                 s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc, s->gbdec2,
-                                                                                s->fired, (SaeScalars*)s->scalars, F, d, s->k)));
+                                                                                s->fired, (SaeScalars*)s->scalars, F, d, s->k, wh, work_feats,
+                                                                                work_chunks)));
   PB_LAUNCH_CHECK();
+  PB_DISPATCH_CHUNKS(ch, (k_sae_grads_long<C_><<<pb_sm_count() * 4, 256, sizeof(float) * d, st>>>(
+                             s->csc_off, s->csc_entries, s->val, s->dval, s->g, s->sae_in, s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc,
+                             s->gbdec2, s->fired, d, s->k, wh, work_chunks)));
+  PB_LAUNCH_CHECK();
+  if (!s->dist) {
+    k_sae_norm_long<<<pb_sm_count(), 256, 0, st>>>(s->gW_dec, s->gW_encT, s->gb_enc, (SaeScalars*)s->scalars, d, wh, work_feats);
+    PB_LAUNCH_CHECK();
+  }
   if (s->dist) {  // data parallel: only the local gb_dec; norm / clip happen after the peer reduction (p2p.cu)
     k_sae_gbdec<<<(d + 255) / 256, 256, 0, st>>>(s->gcol, s->gbdec2, s->gb_dec, d);
     PB_LAUNCH_CHECK();

@@ -34,7 +34,7 @@ class PbSaeStep(C.Structure):
             "csc_off", "csc_cursor", "csc_entries", "gW_dec", "gW_encT", "gb_enc", "gb_dec", "gcol", "gbdec2",
             "fired", "scalars", "m_dec", "v_dec", "m_enc", "v_enc", "m_be", "v_be", "m_bd", "v_bd",
             "since_fired", "act_freq")]
-        + [("global_rows", i32), ("dist", i32)]
+        + [("global_rows", i32), ("dist", i32), ("work", vp), ("work_bytes", i64)]
     )
 
 
@@ -161,6 +161,7 @@ class SaeStepEngine:
         self.hidden_pre = e(rows, F)
         self.idx, self.val, self.dval = e(rows, k, dt=torch.int32), e(rows, k), e(rows, k)
         self.csc_entries = e(rows * k, dt=torch.int32)
+        self.work = e(8 + 4 * F + 8 * (rows * k // 32 + F + 1) + 64, dt=torch.uint8)   # hot-feature work lists (pb_sae_backward)
         nseg = (F + TOPK_SEG - 1) // TOPK_SEG
         self.topk_scratch = e(max(rows * nseg * k * 8, 16), dt=torch.uint8) if F > TOPK_SEG else None
         self._rows = rows
@@ -182,6 +183,7 @@ class SaeStepEngine:
         s.m_dec, s.v_dec, s.m_enc, s.v_enc = p(self.m_dec), p(self.v_dec), p(self.m_enc), p(self.v_enc)
         s.m_be, s.v_be, s.m_bd, s.v_bd = p(self.m_be), p(self.v_be), p(self.m_bd), p(self.v_bd)
         s.since_fired, s.act_freq = p(since_fired), p(act_freq)
+        s.work, s.work_bytes = p(self.work), self.work.numel()
         return s
 
     # ------------------------------------------------------------------ pieces

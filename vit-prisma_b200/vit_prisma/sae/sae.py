@@ -242,6 +242,23 @@ class StandardSparseAutoencoder(SparseAutoencoder):
             self._engine = eng
         return eng
 
+    def enable_data_parallel(self, group, gemm_impl: int = L.GEMM_AUTO):
+        """Move the parameters into NVLink peer-visible buffers and make ``step_engine()`` return the data-parallel engine
+        (vit_prisma/b200/p2p.py): every rank then feeds its own token shard to ``train_step`` and all ranks hold identical
+        parameters after each step.  ``group`` is a ``P2PGroup`` (one process per GPU)."""
+        from vit_prisma.b200.p2p import SaeDPEngine
+        if self.cfg.activation_fn_str != "topk":
+            raise NotImplementedError("the fused step engine covers activation_fn_str == 'topk'")
+        wt, wd, be, bd = self._canonical_params()
+        eng = SaeDPEngine(group, wt.contiguous(), wd, be, bd, k=self.cfg.activation_fn_kwargs["k"], normalize_activations=self._norm_mode,
+                          max_grad_norm=self.cfg.max_grad_norm, gemm_impl=gemm_impl)
+        # the nn.Parameters become views of the shared buffers, so state_dict()/save_model() see what the kernels update
+        self.W_enc.data, self.W_dec.data, self.b_enc.data, self.b_dec.data = eng.W_encT.t(), eng.W_dec, eng.b_enc, eng.b_dec
+        eng._key = (eng.W_encT.data_ptr(), eng.W_dec.data_ptr(), eng.b_enc.data_ptr(), eng.b_dec.data_ptr(), gemm_impl)
+        eng._enc_version = self.W_enc._version
+        self._engine = eng
+        return eng
+
     def _hooks_attached(self) -> bool:
         return not all(hp.is_inert for hp in self.hook_points())
 

@@ -62,8 +62,9 @@ class FusedSchedule:
 
 
 class VisionSAETrainer:
-    def __init__(self, cfg: VisionModelSAERunnerConfig, model, dataset, eval_dataset=None, activations_store=None):
+    def __init__(self, cfg: VisionModelSAERunnerConfig, model, dataset, eval_dataset=None, activations_store=None, p2p_group=None):
         self.cfg = cfg
+        self.p2p_group = p2p_group       # vit_prisma.b200.p2p.P2PGroup: data-parallel training, one process per GPU
         self.is_transcoder = cfg.is_transcoder
         for attr in ("min_l0", "min_explained_variance"):          # older configs may lack these
             if not hasattr(cfg, attr):
@@ -135,6 +136,21 @@ class VisionSAETrainer:
             self.sparse_coder.initialize_b_dec_with_mean(acts)
         self.sparse_coder.train()
         return medians
+
+    def _canonical_param_storages(self):
+        """Contiguous tensors behind the four parameters (W_enc is a transposed view of a [d_sae, d_in] buffer)."""
+        wt, wd, be, bd = self.sparse_coder._canonical_params()
+        return [wt, wd, be, bd]
+
+    def enable_data_parallel_if_requested(self):
+        """With a P2PGroup: rank 0's b_dec initialisation is broadcast (every rank must start from identical parameters),
+        then the parameters move into NVLink peer-visible buffers (sae.enable_data_parallel)."""
+        if self.p2p_group is None or self.p2p_group.world == 1:
+            return
+        import torch.distributed as dist
+        for prm in self._canonical_param_storages():
+            dist.broadcast(prm, src=0)
+        self.sparse_coder.enable_data_parallel(self.p2p_group)
 
     # ------------------------------------------------------------------ one step
     def train_step(self, sparse_autoencoder, optimizer, scheduler, act_freq_scores, n_forward_passes_since_fired,
@@ -208,6 +224,7 @@ class VisionSAETrainer:
             self.initalize_wandb()
         act_freq_scores, since_fired, n_frac_active_tokens, optimizer, scheduler = self.initialize_training_variables()
         self.initialize_geometric_medians()
+        self.enable_data_parallel_if_requested()
         n_steps, n_tokens = 0, 0
         progress_every = progress_every or max(self.cfg.wandb_log_frequency, 1)
         pbar = tqdm(total=self.cfg.total_training_tokens, desc="Training SAE", mininterval=20)
