@@ -150,6 +150,18 @@ def test_attention_fused_and_split(B, T, H, dh, dtype):
     assert rel_err(pt3.float(), pt.float()) < tol and rel_err(z3.float(), z.float()) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_scale_not_power_of_two(dtype):
+    """d_head 64 with attn_scale 7.3: the tensor-core kernel must take its true-division branch (scores = dot / scale)."""
+    ops = _ops()
+    q, k, v = (_rand(2, 50, 3, 64, seed=s, dtype=dtype) for s in (4, 5, 6))
+    sc_ref = (torch.einsum("bqhe,bkhe->bhqk", q.float(), k.float()).to(dtype).float() / 7.3).to(dtype)
+    pt_ref = F.softmax(sc_ref.float(), dim=-1).to(dtype)
+    sc, pt, _ = ops.attention(q.cuda(), k.cuda(), v.cuda(), 7.3)
+    tol = 1e-5 if dtype == torch.float32 else 1.2e-2
+    assert rel_err(sc.float(), sc_ref.float()) < tol and rel_err(pt.float(), pt_ref.float()) < tol
+
+
 def test_softmax_nan_to_zero():
     ops = _ops()
     x = torch.zeros(2, 4, device="cuda")

@@ -18,6 +18,7 @@ struct EpiParams {
   int n_split, split_n;
   void* out_split[4];
   int vec_ok;
+  int vec16_ok;   // every output / residual row segment of 32 columns is a whole number of aligned 16-byte vectors
 };
 
 template <typename T>
@@ -99,5 +100,9 @@ static inline EpiParams pb_make_epi(const PbGemm* g) {
     for (int i = 0; i < ep.n_split; ++i) v = v && pb_aligned16(g->out_split[i]);
   }
   ep.vec_ok = v ? 1 : 0;
+  const int e16 = g->dtype == PB_BF16 ? 8 : 4;   // elements per 16 bytes
+  bool w = v && (g->ld0 % e16 == 0) && (g->ld1 % e16 == 0) && (g->ldr % e16 == 0);
+  if (ep.n_split > 1) w = w && (g->split_n % 32 == 0);
+  ep.vec16_ok = w ? 1 : 0;
   return ep;
 }

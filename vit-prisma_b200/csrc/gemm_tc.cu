@@ -293,7 +293,8 @@ template <typename T, int NPASS, int BN, int STAGES, int NEPI>
 struct Tc2Cfg {
   using Base = TcCfg<T, NPASS, BN, STAGES>;
   static constexpr int THREADS = 64 + NEPI * 32;
-  static constexpr int EPI_STAGE_BYTES = NEPI * 32 * 33 * 4;
+  static constexpr int EPI_WARP_FLOATS = sizeof(T) == 2 ? 32 * 33 : 32 * 36;
+  static constexpr int EPI_STAGE_BYTES = NEPI * EPI_WARP_FLOATS * 4;   // 32x33 fp32 transposer (tail path) / 32 rows x 144 B vector stage
   static constexpr int SMEM_BYTES = Base::RING_BYTES + EPI_STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
@@ -343,14 +344,18 @@ __device__ __forceinline__ void ld2(const bf16* p, float& a, float& b) {
 // GELU(x) = x/2 (1 + erf(x/sqrt2)) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, branch-free, one
 // MUFU.EX2 + one MUFU.RCP): the epilogue of the MLP-in GEMM evaluates it B*T*d_mlp times per block and was issue-bound
 // on libdevice's branchy erff (profiles/r01_gemm_notes.md).  Absolute error of the result <= 0.75e-7 |x|.
+__device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float gelu_fast(float x) {
+  // single MUFU.RCP / MUFU.EX2, no IEEE fix-up branches: __frcp_rn's slow path put a BSSY/BSYNC pair around every element,
+  // which serialised the 32 unrolled evaluations (0.265 ms -> see profiles/r01_gemm_notes.md)
   const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  const float t = mufu_rcp(fmaf(0.3275911f, ax, 1.f));
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);
   p = fmaf(t, p, 0.254829592f);
-  const float erf_abs = fmaf(-p * t, __expf(-ax * ax), 1.f);
+  const float erf_abs = fmaf(-p * t, mufu_ex2(ax * ax * -1.4426950408889634f), 1.f);
   return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
 
@@ -420,6 +425,141 @@ __device__ __forceinline__ void epi_rows_pair(const EpiParams& ep, const float* 
   else if (mode == EPI_GELU) PB_EPI(EPI_GELU);
   else PB_EPI(EPI_ACT);
 #undef PB_EPI
+}
+
+// ---- v3 epilogue: arithmetic in TMEM's native layout, shared memory only as a 16-byte-vector transposer ----------------
+// tcgen05.ld gives thread t row t of a 32x32 chunk.  Bias / rounding / GELU / residual are applied right there (constant
+// register indices, no per-element address arithmetic); the packed results are written as the thread's row into a padded
+// stage (row stride 32*sizeof(T)+16 B: conflict-free for 128-bit accesses) and copied out with 16 B loads/stores where
+// consecutive lanes cover consecutive 16 B of a row.  ~20 instructions per element against ~56 for the per-element walk
+// (profiles/r01_gemm_notes.md), and every global access is a full 16 B vector of a contiguous row segment.
+template <typename T> struct EpiStage {
+  static constexpr int VPR = 32 * (int)sizeof(T) / 16;        // 16-byte vectors per 32-column row: 4 (bf16) / 8 (fp32)
+  static constexpr int ROW_BYTES = 32 * (int)sizeof(T) + 16;
+};
+
+__device__ __forceinline__ void stage_put_row(uint8_t* row, const float (&v)[32], float) {   // fp32 rows
+#pragma unroll
+  for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(row + 16 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void stage_put_row(uint8_t* row, const float (&v)[32], bf16) {    // bf16 rows
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]), p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]), p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(row + 16 * q) = u;
+  }
+}
+__device__ __forceinline__ void stage_get_row(const uint8_t* row, float (&v)[32], float) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(row + 16 * q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void stage_get_row(const uint8_t* row, float (&v)[32], bf16) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + 16 * q);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[8 * q + 2 * j] = __uint_as_float(w[j] << 16);
+      v[8 * q + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+  }
+}
+
+// stage (32 rows x 32 cols of T) -> global rows [row0, row0+nrows) x cols [col, col+32): 16 B per lane per trip
+template <typename T>
+__device__ __forceinline__ void stage_copy_out(const uint8_t* stage, T* __restrict__ gbase, int64_t ld, int lane, int nrows) {
+  constexpr int VPR = EpiStage<T>::VPR;
+#pragma unroll
+  for (int i = 0; i < VPR; ++i) {
+    const int vidx = lane + 32 * i, row = vidx / VPR, vin = vidx % VPR;
+    if (row < nrows)
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbase + (int64_t)row * ld) + 16 * vin) =
+          *reinterpret_cast<const uint4*>(stage + row * EpiStage<T>::ROW_BYTES + 16 * vin);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void stage_copy_in(uint8_t* stage, const T* __restrict__ gbase, int64_t ld, int lane, int nrows) {
+  constexpr int VPR = EpiStage<T>::VPR;
+#pragma unroll
+  for (int i = 0; i < VPR; ++i) {
+    const int vidx = lane + 32 * i, row = vidx / VPR, vin = vidx % VPR;
+    if (row < nrows)
+      *reinterpret_cast<uint4*>(stage + row * EpiStage<T>::ROW_BYTES + 16 * vin) =
+          *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(gbase + (int64_t)row * ld) + 16 * vin);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void epi_chunk_vec(const EpiParams& ep, const uint32_t (&r)[32], uint8_t* stage, int lane, int row0, int nrows,
+                                              int col0) {
+  uint8_t* my_row = stage + lane * EpiStage<T>::ROW_BYTES;
+  float v[32];
+  const T* bias = (const T*)ep.bias;
+  if (bias) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float bb[4];
+      ld4(bias + col0 + 4 * q, bb);                              // same address in every lane: one broadcast transaction
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[4 * q + j] = round_to<T>(__uint_as_float(r[4 * q + j]) + bb[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = round_to<T>(__uint_as_float(r[j]));
+  }
+  // ---- out0 (or the q / k / v block this chunk falls into)
+  T* o0 = nullptr;
+  if (ep.n_split > 1) {
+    const int blk = col0 / ep.split_n;
+    void* base = blk == 0 ? ep.out_split[0] : blk == 1 ? ep.out_split[1] : blk == 2 ? ep.out_split[2] : ep.out_split[3];
+    o0 = (T*)base + (col0 - blk * ep.split_n);
+  } else if (ep.out0) {
+    o0 = (T*)ep.out0 + col0;
+  }
+  if (o0) {
+    stage_put_row(my_row, v, T());
+    __syncwarp();
+    stage_copy_out<T>(stage, o0 + (int64_t)row0 * ep.ld0, ep.ld0, lane, nrows);
+    __syncwarp();
+  }
+  if (!ep.out1) return;
+  // ---- out1 = residual + v  |  act(v)
+  if (ep.residual) {
+    stage_copy_in<T>(stage, (const T*)ep.residual + (int64_t)row0 * ep.ldr + col0, ep.ldr, lane, nrows);
+    __syncwarp();
+    float rs[32];
+    stage_get_row(my_row, rs, T());
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = rs[j] + v[j];
+  } else if (ep.act == PB_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+  } else {
+    const int act = ep.act;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], act);
+  }
+  stage_put_row(my_row, v, T());
+  __syncwarp();
+  stage_copy_out<T>(stage, (T*)ep.out1 + (int64_t)row0 * ep.ld1 + col0, ep.ld1, lane, nrows);
+  __syncwarp();
+  if (sizeof(T) == 4 && ep.out1_lo) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] - tf32_trunc(v[j]);
+    stage_put_row(my_row, v, T());
+    __syncwarp();
+    stage_copy_out<T>(stage, (T*)ep.out1_lo + (int64_t)row0 * ep.ld1 + col0, ep.ld1, lane, nrows);
+    __syncwarp();
+  }
 }
 
 template <typename T, int NPASS, int BN, int STAGES, int NEPI>
@@ -525,7 +665,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const int quarter = warp & 3;                // TMEM lane quarter this warp may read
     constexpr int CPW = BN / (NEPI / 4);         // columns per epilogue warp
     const int cbase = (e / 4) * CPW;
-    float* stage = reinterpret_cast<float*>(smem_raw + (epi_stage - smem0)) + e * (32 * 33);
+    float* stage = reinterpret_cast<float*>(smem_raw + (epi_stage - smem0)) + e * C2::EPI_WARP_FLOATS;
     int li = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
       const int m0 = (tile / num_n_tiles) * TC_BM, n0 = (tile % num_n_tiles) * BN;
@@ -545,15 +685,19 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(ab));
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
-        __syncwarp();
         const int col0 = n0 + cbase + c * 32;
-        if (nrows > 0) {
-          if (ep.vec_ok) epi_rows_pair<T>(ep, stage, lane, row0, nrows, col0);
-          else if (col0 + lane < ep.N) epi_rows_scalar<T>(ep, stage, lane, row0, nrows, col0 + lane);
+        if (ep.vec16_ok && col0 + 32 <= ep.N) {     // whole chunk inside the matrix: native-layout epilogue
+          if (nrows > 0) epi_chunk_vec<T>(ep, r, reinterpret_cast<uint8_t*>(stage), lane, row0, nrows, col0);
+        } else {                                     // ragged edge / unaligned operands: per-element walk
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          if (nrows > 0) {
+            if (ep.vec_ok) epi_rows_pair<T>(ep, stage, lane, row0, nrows, col0);
+            else if (col0 + lane < ep.N) epi_rows_scalar<T>(ep, stage, lane, row0, nrows, col0 + lane);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -682,7 +826,7 @@ int pb_gemm_tc(const PbGemm* g, cudaStream_t st) {
     if (variant != 1 && g->N >= 128) return launch_tc2<bf16, 1, 128, 4, 4>(g, st);
     return launch_tc<bf16, 1, 128, 3>(g, st);
   }
-  if (variant == 2 && g->N >= 256) return launch_tc2<float, 3, 256, 2, 8>(g, st);   // wider tile, shallower ring (A/B)
+  if (variant == 2 && g->N >= 256) return launch_tc2<float, 3, 256, 2, 4>(g, st);   // wider tile, shallower ring (A/B)
   if (variant != 1) return launch_tc2<float, 3, 128, 3, 4>(g, st);
   return launch_tc<float, 3, 128, 3>(g, st);
 }
