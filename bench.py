@@ -261,20 +261,22 @@ def run_ours(args):
 
     # ---- end to end: pinned host batch -> H2D -> run_with_cache -> D2H of the model output, every step
     out_host = torch.empty((B, CLIP_B32["n_classes"]), dtype=dtype).pin_memory()
-    for _ in range(2):
-        xd = host.to(dev, non_blocking=True)
+    # (the copy of batch i+1 runs on a side stream under batch i's forward -- vit_prisma.b200.prefetch.DevicePrefetcher, the
+    # loader-side helper the package ships; every step's bytes still cross PCIe inside the timed region)
+    from vit_prisma.b200.prefetch import DevicePrefetcher
+    for xd in DevicePrefetcher((host for _ in range(2)), dev):
         out, cache = model.run_with_cache(xd)
         out_host.copy_(out, non_blocking=True)
         del cache
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        xd = host.to(dev, non_blocking=True)
+    for xd in DevicePrefetcher((host for _ in range(args.steps)), dev):
         out, cache = model.run_with_cache(xd)
         out_host.copy_(out, non_blocking=True)
         del cache
     e1.record()
+    del xd
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
 
@@ -307,7 +309,8 @@ def run_ours(args):
                        "parallelism": f"dp{world} (images sharded, no collective)"},
             "clocks": clocks.summary(), "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * host.element_size()),
-                    "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()), "ms_per_step": e2e_ms / args.steps,
+                    "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
@@ -411,15 +414,14 @@ def run_sae(args):
     launches = L.get_lib().pb_launch_count() - l0
     # e2e: pinned host tokens -> H2D -> step -> D2H of the step scalars (mse, l0, grad norm, ...)
     sc_host = torch.empty(8).pin_memory()
-    xin = torch.empty(Bt, d, device=dev)
-    for i in range(2):
-        xin.copy_(pool_host[(i % 16) * Bt:(i % 16 + 1) * Bt], non_blocking=True)
+    from vit_prisma.b200.prefetch import DevicePrefetcher
+    host_batches = lambda n: (pool_host[(i % 16) * Bt:(i % 16 + 1) * Bt] for i in range(n))
+    for xin in DevicePrefetcher(host_batches(2), dev):
         sc_host.copy_(eng.train_step(xin, lr, since_fired, act_freq), non_blocking=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        xin.copy_(pool_host[(i % 16) * Bt:(i % 16 + 1) * Bt], non_blocking=True)
+    for xin in DevicePrefetcher(host_batches(args.steps), dev):
         sc_host.copy_(eng.train_step(xin, lr, since_fired, act_freq), non_blocking=True)
     e1.record()
     barrier()
@@ -470,7 +472,7 @@ def run_sae(args):
                                                        f"{int((world - 1) / world * (2 * d * F * 4 * 2 + d * F * 4) / 1e6)} MB over NVLink per GPU per step)" if world > 1 else "")},
             "clocks": clocks.summary(), "gpu_launches": int(launches),
             "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * 4, "d2h_bytes_per_step": 32,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps, "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 

@@ -36,13 +36,17 @@ if __name__ == "__main__":
         probe(25600, 3072, 768, torch.bfloat16, ["pre+gelu"]); sys.exit(0)
     if which == "one32":
         probe(25600, 3072, 768, torch.float32, ["pre+gelu"]); sys.exit(0)
-    probe(25600, 3072, 768, torch.bfloat16, ["pre_nobias", "pre", "pre+gelu", "gelu_only", "torch", "simt"])
+    probe(25600, 3072, 768, torch.bfloat16, ["pre_nobias", "pre", "pre+gelu", "gelu_only", "torch"])
     probe(25600, 768, 3072, torch.bfloat16, ["pre", "pre+resid", "torch"])
     probe(25600, 2304, 768, torch.bfloat16, ["pre", "torch"])
-    probe(25600, 3072, 768, torch.float32, ["pre", "pre+gelu", "simt", "torch"])
-    probe(4096, 24576, 768, torch.float32, ["pre", "simt"])
-    if which == "cpu":
-        pass
+    probe(25600, 3072, 768, torch.float32, ["pre", "pre+gelu", "torch"])
+    probe(25600, 768, 768, torch.bfloat16, ["pre", "pre+resid", "torch"])
+    probe(25600, 768, 3072, torch.float32, ["pre", "pre+resid"])
+    probe(25600, 2304, 768, torch.float32, ["pre"])
+    probe(25600, 768, 768, torch.float32, ["pre", "pre+resid"])
+    probe(4096, 24576, 768, torch.float32, ["pre"])
+    if which != "cpu":
+        sys.exit(0)
     # host-thread calibration for the CPU baseline
     from oracle.vit_oracle import CLIP_B32, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
     sd = recipe_state_dict(state_dict_shapes(CLIP_B32), 1234); x = torch.randn(8, 3, 224, 224)
