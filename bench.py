@@ -42,46 +42,57 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md), through NVML in this process.
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    NVML is initialised when the sampler is constructed (before the warm-up steps): starting `nvidia-smi` next to the timed
+    loop costs seconds of driver initialisation that stall this process's own launches, and its first sample arrives after a
+    short timed region is already over.  The polling thread sleeps between reads; only samples taken between __enter__ and
+    __exit__ are reported."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __enter__(self):
+    def __init__(self, index=0, period_s=0.02):
+        self.rows, self.active, self.stop, self.period = [], False, False, period_s
+        self.h = self.nv = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.h, self.nv = pynvml.nvmlDeviceGetHandleByIndex(phys), pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
-            self.proc = None
-        return self
+            self.h = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        nv = self.nv
+        while not self.stop:
+            if self.active:
+                try:
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(mask)))
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        self.active = True
+        return self
 
     def __exit__(self, *exc):
-        if self.proc:
-            self.proc.terminate()
+        self.active = False
+
+    def close(self):
+        self.stop = True
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            parts = [p.strip() for p in r.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx = max(mx, float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({name for _, mask in self.rows for name, bit in self.REASONS if mask & bit})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": getattr(self, "max_mhz", None) if self.h else None,
+                "reasons": reasons, "samples": len(sm), "source": "nvml (in-process, polled during the timed region)" if self.h else "unavailable"}
 
 
 def _dist():
@@ -240,13 +251,14 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident throughput
+    clocks = ClockSampler(local)
     for _ in range(args.warmup):
         out, cache = model.run_with_cache(x)
         del cache
     barrier()
     n_keys = 0
     launches0 = L.get_lib().pb_launch_count()
-    with ClockSampler(local) as clocks:
+    with clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
@@ -256,6 +268,7 @@ def run_ours(args):
         e1.record()
         barrier()
         dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks.close()
     launches = L.get_lib().pb_launch_count() - launches0
     route = model.last_route
 
@@ -271,14 +284,19 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks = []
     for xd in DevicePrefetcher((host for _ in range(args.steps)), dev):
         out, cache = model.run_with_cache(xd)
         out_host.copy_(out, non_blocking=True)
         del cache
+        if os.environ.get("PRISMA_BENCH_DEBUG"):
+            marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
     e1.record()
     del xd
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    if marks:
+        print("e2e per-step ms:", [round(a.elapsed_time(b), 2) for a, b in zip([e0] + marks[:-1], marks)], file=sys.stderr)
 
     if rank != 0:
         return
@@ -399,18 +417,22 @@ def run_sae(args):
         j = (i % 16) * Bt
         return pool[j:j + Bt]
 
+    clocks = ClockSampler(local)
     for i in range(args.warmup):
         eng.train_step(batch(i), lr, since_fired, act_freq)
     barrier()
     l0 = L.get_lib().pb_launch_count()
-    with ClockSampler(local) as clocks:
+    with clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for i in range(args.steps):
             eng.train_step(batch(i), lr, since_fired, act_freq)
         e1.record()
+        host_enqueue_ms = 1e3 * (time.perf_counter() - t_host) / args.steps
         barrier()
         dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks.close()
     launches = L.get_lib().pb_launch_count() - l0
     # e2e: pinned host tokens -> H2D -> step -> D2H of the step scalars (mse, l0, grad norm, ...)
     sc_host = torch.empty(8).pin_memory()
@@ -421,9 +443,11 @@ def run_sae(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for xin in DevicePrefetcher(host_batches(args.steps), dev):
         sc_host.copy_(eng.train_step(xin, lr, since_fired, act_freq), non_blocking=True)
     e1.record()
+    e2e_host_ms = 1e3 * (time.perf_counter() - t_host) / args.steps
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     if rank != 0:
@@ -470,9 +494,10 @@ def run_sae(args):
                        "l2": "working set (2 x 75 MB weights + 2 x 150 MB Adam state + 150 MB grads + 403 MB hidden_pre) larger than L2",
                        "parallelism": f"dp{world}" + (" (NVLink peer-memory reduce-scatter + sharded Adam + all-gather, no NCCL on the data path; "
                                                        f"{int((world - 1) / world * (2 * d * F * 4 * 2 + d * F * 4) / 1e6)} MB over NVLink per GPU per step)" if world > 1 else "")},
-            "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "clocks": clocks.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
             "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * 4, "d2h_bytes_per_step": 32,
-                    "ms_per_step": e2e_ms / args.steps, "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
+                    "ms_per_step": e2e_ms / args.steps, "host_enqueue_ms_per_step": e2e_host_ms,
+                    "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 

@@ -84,6 +84,16 @@ def test_gemm_tc_3xtf32_matches_fp32(M, N, K):
     assert rel_err(post_t, ref + r.cpu()) < 3e-5
 
 
+def test_gemm_tc_3xtf32_m_fast_raster():
+    """Dictionary-sized B (> 48 MB with its lo plane) flips the persistent kernel to the m-fastest tile walk (SAE encoder shape)."""
+    ops, L = _ops(), _L()
+    M, N, K = 520, 24576, 768
+    a, w, b = _rand(M, K, seed=1).cuda(), _rand(N, K, seed=2, scale=K ** -0.5).cuda(), _rand(N, seed=3).cuda()
+    pre_t, _ = ops.gemm(a, w, b, a_lo=ops.split_tf32(a), w_lo=ops.split_tf32(w), impl=L.GEMM_TC)
+    ref = torch.addmm(b.double(), a.double(), w.double().t()).float()
+    assert rel_err(pre_t, ref) < 3e-5
+
+
 def test_gemm_split_outputs_qkv():
     ops, L = _ops(), _L()
     import ctypes as C

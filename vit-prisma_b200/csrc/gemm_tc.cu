@@ -565,9 +565,14 @@ __device__ __forceinline__ void epi_chunk_vec(const EpiParams& ep, const uint32_
 template <typename T, int NPASS, int BN, int STAGES, int NEPI>
 __global__ void __launch_bounds__(64 + NEPI * 32, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAlo,
-           const __grid_constant__ CUtensorMap tmBlo, int K, EpiParams ep, int num_m_tiles, int num_n_tiles) {
+           const __grid_constant__ CUtensorMap tmBlo, int K, EpiParams ep, int num_m_tiles, int num_n_tiles, int m_fast) {
   using C = TcCfg<T, NPASS, BN, STAGES>;
   using C2 = Tc2Cfg<T, NPASS, BN, STAGES, NEPI>;
+  // raster order of the persistent tile walk: the ~148 tiles in flight share one operand through L2 and stream the other.
+  // n-fastest (default) streams A once and wants B (the weights) L2-resident; m_fast streams B once and keeps A resident --
+  // the SAE encoder (A = 4096 tokens, B = 24576 x 768 dictionary, 151 MB with its lo plane) needs the latter.
+  auto tile_m = [&](int tile) { return m_fast ? tile % num_m_tiles : tile / num_n_tiles; };
+  auto tile_n = [&](int tile) { return m_fast ? tile / num_m_tiles : tile % num_n_tiles; };
   constexpr int KIND = sizeof(T) == 2 ? 0 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = smem_u32(smem_raw);
@@ -606,7 +611,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_tiles) * TC_BM, n0 = (tile % num_n_tiles) * BN;
+        const int m0 = tile_m(tile) * TC_BM, n0 = tile_n(tile) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -668,7 +673,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     float* stage = reinterpret_cast<float*>(smem_raw + (epi_stage - smem0)) + e * C2::EPI_WARP_FLOATS;
     int li = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++li) {
-      const int m0 = (tile / num_n_tiles) * TC_BM, n0 = (tile % num_n_tiles) * BN;
+      const int m0 = tile_m(tile) * TC_BM, n0 = tile_n(tile) * BN;
       const int ab = li & 1;
       const uint32_t aph = (li >> 1) & 1;
       mbar_wait(tfull_bar(ab), aph);
@@ -793,7 +798,10 @@ int launch_tc2(const PbGemm* g, cudaStream_t st) {
   const int num_m = (g->M + TC_BM - 1) / TC_BM, num_n = (g->N + BN - 1) / BN;
   int grid = pb_sm_count();
   if (grid > num_m * num_n) grid = num_m * num_n;
-  kern<<<grid, C2::THREADS, C2::SMEM_BYTES, st>>>(tmA, tmB, tmAlo, tmBlo, g->K, ep, num_m, num_n);
+  const size_t planes = NPASS > 1 ? 2 : 1;
+  const size_t a_bytes = (size_t)g->M * g->K * sizeof(T) * planes, b_bytes = (size_t)g->N * g->K * sizeof(T) * planes;
+  const int m_fast = (b_bytes > ((size_t)48 << 20) && a_bytes < b_bytes) ? 1 : 0;
+  kern<<<grid, C2::THREADS, C2::SMEM_BYTES, st>>>(tmA, tmB, tmAlo, tmBlo, g->K, ep, num_m, num_n, m_fast);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
