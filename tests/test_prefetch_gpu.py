@@ -27,3 +27,19 @@ def test_prefetcher_order_and_content():
     # a second pass over fewer batches than the depth
     out = [x.clone() for x in DevicePrefetcher(host[:1], dev)]
     assert len(out) == 1 and torch.equal(out[0].cpu(), host[0])
+
+
+@pytest.mark.gpu
+def test_prefetcher_feed_reuses_buffers_across_passes():
+    from vit_prisma.b200.prefetch import DevicePrefetcher
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(1)
+    host = [torch.randn(8, 16, generator=g).pin_memory() for _ in range(5)]
+    pf = DevicePrefetcher(None, dev)
+    assert list(pf) == []
+    for _ in range(3):
+        got = [x.clone() for x in pf.feed(host)]
+        assert len(got) == 5 and all(torch.equal(a.cpu(), b) for a, b in zip(got, host))
+    ptrs = {b.data_ptr() for b in pf._bufs}
+    list(pf.feed(host[:2]))
+    assert {b.data_ptr() for b in pf._bufs} == ptrs

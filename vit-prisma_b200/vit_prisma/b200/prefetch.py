@@ -14,7 +14,8 @@ import torch
 
 
 class DevicePrefetcher:
-    def __init__(self, batches: Iterable[torch.Tensor], device: torch.device, depth: int = 2, dtype: Optional[torch.dtype] = None):
+    def __init__(self, batches: Optional[Iterable[torch.Tensor]], device: torch.device, depth: int = 2,
+                 dtype: Optional[torch.dtype] = None):
         if torch.device(device).type != "cuda":
             raise RuntimeError("DevicePrefetcher: device must be a CUDA device (the B200 path has no CPU fallback)")
         if depth < 2:
@@ -22,7 +23,7 @@ class DevicePrefetcher:
         self.device = torch.device(device)
         self.depth = depth
         self.dtype = dtype
-        self._it = iter(batches)
+        self._it = iter(batches) if batches is not None else iter(())
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._bufs: list[Optional[torch.Tensor]] = [None] * depth
         self._ready = [torch.cuda.Event() for _ in range(depth)]       # copy into slot finished
@@ -32,6 +33,15 @@ class DevicePrefetcher:
         self._tail = 0          # next slot to hand out
         self._inflight = 0
         self._exhausted = False
+
+    def feed(self, batches: Iterable[torch.Tensor]) -> "DevicePrefetcher":
+        """Start a new pass over ``batches`` with the same stream and device buffers (a loader object lives across epochs:
+        stream creation and the first cudaMalloc of the staging buffers are set-up cost, not per-batch work)."""
+        if self._inflight:
+            raise RuntimeError("DevicePrefetcher.feed: the previous pass still has batches in flight")
+        self._it = iter(batches)
+        self._exhausted = False
+        return self
 
     def _issue(self) -> None:
         try:
