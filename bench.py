@@ -309,8 +309,16 @@ def run_ours(args):
     flops_img = vit_flops_per_image(CLIP_B32)
     # fp32 mode executes 3 tensor-core passes per algorithmic flop; the roofline counts ALGORITHMIC flops
     achieved = kern["flops"] / (kern["ms"] / 1e3) / 1e12
-    roof = {"bound": "tensor", "kernel": "k_gemm_tc (MLP-in GEMM + bias + GELU, hook_pre/hook_post spill)", "achieved": achieved,
-            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from one `ncu --set full` capture (profiles/r01_gemm_fp32_ncu_summary.txt,
+    # profiles/r01_gemm_bf16_v3_ncu_summary.txt); algorithmic: A (+ lo plane) + weights read, two M x N outputs written
+    traffic = (180.070400e6 + 580.768512e6) if dtype == torch.float32 else (44.133632e6 + 262.480640e6)
+    roof = {"bound": "tensor", "kernel": "k_gemm_tc2 (MLP-in GEMM + bias + GELU, hook_pre/hook_post spill)", "achieved": achieved,
+            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+            "traffic_unit": "B/launch (ncu dram read+write)", "algorithmic_bytes": kern["bytes"],
+            "executed_tensor_tflops": achieved * (3 if dtype == torch.float32 else 1),
+            "note": ("fp32 = 3 TF32 passes per algorithmic flop at half the bf16 MMA rate: ncu shows the tensor pipe 71.5 % active "
+                     "on this launch (profiles/r01_gemm_fp32_ncu_summary.txt); frac is algorithmic flops over the bf16 peak") if dtype == torch.float32 else
+                    "ncu: tensor pipe 36.6 % active, issue slots 50.6 % (profiles/r01_gemm_bf16_v3_ncu_summary.txt)",
             "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)", "shape_MNK": kern["shape"], "kernel_ms": kern["ms"],
             "hbm_gbs_of_kernel": kern["bytes"] / (kern["ms"] / 1e3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
             "passes": 3 if dtype == torch.float32 else 1,
@@ -480,11 +488,21 @@ def run_sae(args):
     tokens = world * Bt * args.steps
     value = tokens / (dev_ms / 1e3)
     step_bytes = eng.algorithmic_bytes(Bt)
+    timed("encoder GEMM alone (hidden_pre = sae_in @ W_enc + b_enc, 3xTF32)", lambda: eng._encoder_gemm(Bt))
     adam_bytes = 60 * d * F            # per matrix element pair: g,p,m,v read (16 B) + p,m,v write (12 B) (x2) + tf32 residual write (4 B)
     adam_gbs = adam_bytes / (stages["adam (clip + projection + Adam + renorm)"] / 1e3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_sae_adam_rows (clip + decoder-parallel-grad removal + Adam + row renorm)", "achieved": adam_gbs,
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": adam_gbs / peaks["hbm_gbs"], "traffic": None,
-            "peak_source": peaks["source"] + " copy bandwidth", "algorithmic_bytes_per_launch": adam_bytes,
+    gemm_ms = stages["encoder GEMM alone (hidden_pre = sae_in @ W_enc + b_enc, 3xTF32)"]
+    gemm_tflops = 2.0 * Bt * d * F / (gemm_ms / 1e3) / 1e12
+    # dominant kernel of the step (41 % of the launch time, profiles/r01_launches_sae_v2.txt): the fp32-grade encoder GEMM.
+    # The step as a whole is the HBM-bound object SURVEY 8d describes; its bytes and the Adam kernel's are reported beside it.
+    roof = {"bound": "tensor", "kernel": "k_gemm_tc2<float,3,128,3,4> (encoder GEMM, 3 TF32 passes, m-fastest raster)", "achieved": gemm_tflops,
+            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": None,
+            "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)", "kernel_ms": gemm_ms, "passes": 3,
+            "executed_tensor_tflops": 3 * gemm_tflops, "shape_MNK": [Bt, F, d],
+            "hbm_kernel": {"kernel": "k_sae_adam_rows (clip + decoder-parallel-grad removal + Adam + row renorm)", "achieved": adam_gbs,
+                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": adam_gbs / peaks["hbm_gbs"],
+                           "algorithmic_bytes_per_launch": adam_bytes, "traffic": 604.774912e6 + 474.265088e6,
+                           "traffic_source": "ncu dram read+write, profiles/r01_sae_step_ncu_summary.txt"},
             "step_algorithmic_bytes": step_bytes, "step_hbm_gbs": step_bytes / (dev_ms / args.steps / 1e3) / 1e9,
             "step_hbm_frac": step_bytes / (dev_ms / args.steps / 1e3) / 1e9 / peaks["hbm_gbs"], "stage_ms": stages}
     cpu = cpu_sae_tokens_per_sec()

@@ -1,4 +1,5 @@
-"""ORACLE (test infrastructure, not product code): CPU restatement of the TopK SAE forward and training step.
+"""ORACLE (test infrastructure, not product code): CPU restatement of the SAE forward and training step
+(TopK and dense ReLU + L1 activations, optional ghost-grad auxiliary loss).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this, and only
 as the checker.  Restates, with explicit gradient formulas instead of autograd (so the hand-written CUDA backward is
@@ -8,6 +9,8 @@ checked against an independent derivation that is itself pinned to the reference
   run-time input normalisation ("layer_norm")           sae/sae.py:78-90
   _compute_mse_loss                                     sae/sae.py:144-149
   TopK activation                                       sae/sae.py:795-808
+  ReLU activation + L1 sparsity term                    sae/sae.py:617-626, 810-839
+  ghost-grad residual loss on dead features             sae/sae.py:151-179, train_sae.py:330-332
   set_decoder_norm_to_unit_norm / remove_gradient_...   sae/sae.py:275-297
   VisionSAETrainer.train_step ordering, clipping, Adam  sae/train_sae.py:278-411 (torch.optim.Adam defaults)
   cosineannealingwarmup schedule                        sae/training/get_scheduler.py:42-53, train_sae.py:235
@@ -38,28 +41,54 @@ def normalise_in(x: torch.Tensor, mode: str, eps: float = 1e-5):
 
 
 def sae_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, k: int, mode: str = "layer_norm", xbar: Optional[torch.Tensor] = None,
-                global_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                global_rows: Optional[int] = None, act: str = "topk", l1_coefficient: float = 0.0,
+                dead_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """p: W_enc [d,F], W_dec [F,d], b_enc [F], b_dec [d].
     ``xbar`` / ``global_rows``: data-parallel shard view -- batch mean and token count of the GLOBAL batch, so that the
-    shard's loss share and gradients sum over shards to the single-process values."""
+    shard's loss share and gradients sum over shards to the single-process values.
+    ``act``: "topk" | "relu".  ``dead_mask`` [F] bool (not None <=> cfg.use_ghost_grads in training mode): ghost term."""
     xn, mu, std = normalise_in(x, mode)
     sae_in = xn - p["b_dec"]                            # sae.py:564-566
     hidden_pre = sae_in @ p["W_enc"] + p["b_enc"]      # :568-574
-    top = torch.topk(hidden_pre, k=k, dim=-1)           # :803-805
-    vals = torch.relu(top.values)
-    feature_acts = torch.zeros_like(hidden_pre).scatter_(-1, top.indices, vals)   # :806-808
+    if act == "topk":
+        top = torch.topk(hidden_pre, k=k, dim=-1)       # :803-805
+        vals = torch.relu(top.values)
+        feature_acts = torch.zeros_like(hidden_pre).scatter_(-1, top.indices, vals)   # :806-808
+        idx, raw_val = top.indices, top.values
+    elif act == "relu":
+        feature_acts = torch.relu(hidden_pre)           # :810-839 get_activation_fn("relu")
+        idx = raw_val = None
+    else:
+        raise ValueError(act)
     out_n = feature_acts @ p["W_dec"] + p["b_dec"]     # :584-592
     sae_out = out_n * std + mu if mode == "layer_norm" else (out_n * std if mode == "constant_norm_rescale" else out_n)
     x_centred = x - (x.mean(dim=0, keepdim=True) if xbar is None else xbar)   # :145
     nf = torch.norm(x_centred, p=2, dim=-1, keepdim=True)
-    mse = (((sae_out - x) ** 2) / nf).sum() / ((global_rows or x.shape[0]) * x.shape[1])   # :146-148 (.mean())
-    return dict(sae_in=sae_in, hidden_pre=hidden_pre, idx=top.indices, raw_val=top.values, feature_acts=feature_acts,
-                sae_out=sae_out, mse=mse, nf=nf, std=std, mu=mu)
+    rows = global_rows or x.shape[0]
+    mse = (((sae_out - x) ** 2) / nf).sum() / (rows * x.shape[1])   # :146-148 (.mean())
+    l1 = None
+    if act != "topk":                                   # :617-626 (lp_norm = 1)
+        l1 = l1_coefficient * feature_acts.abs().sum(dim=1).sum() / rows
+    out = dict(sae_in=sae_in, hidden_pre=hidden_pre, idx=idx, raw_val=raw_val, feature_acts=feature_acts,
+               sae_out=sae_out, mse=mse, nf=nf, std=std, mu=mu, l1=l1, ghost=torch.zeros(()))
+    if dead_mask is not None:                           # :151-179 _compute_ghost_residual_loss (single-process form)
+        r = x - sae_out
+        rcn = (r - r.mean(dim=0, keepdim=True)).pow(2).sum(dim=-1, keepdim=True).sqrt()
+        l2r = torch.norm(r, dim=-1)
+        E = torch.exp(hidden_pre[:, dead_mask])
+        G0 = E @ p["W_dec"][dead_mask, :]
+        scale = l2r / (1e-6 + torch.norm(G0, dim=-1) * 2)
+        G = G0 * scale[:, None]
+        Lel = (G - r).pow(2) / rcn
+        c = mse / (Lel + 1e-6)
+        out.update(ghost=(c * Lel).mean(), ghost_E=E, ghost_dG0=(c * 2.0 * (G - r) / rcn / Lel.numel()) * scale[:, None])
+    out["loss"] = mse + (l1 if l1 is not None else 0.0) + out["ghost"]
+    return out
 
 
 def sae_grads(p: Dict[str, torch.Tensor], x: torch.Tensor, fwd: Dict[str, torch.Tensor], mode: str = "layer_norm",
-              global_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
-    """Gradients of mse wrt the four parameters, closed form (matches loss.backward() of the reference graph)."""
+              global_rows: Optional[int] = None, l1_coefficient: float = 0.0, dead_mask: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Gradients of the loss wrt the four parameters, closed form (matches loss.backward() of the reference graph)."""
     Bt, d = x.shape
     Bt = global_rows or Bt
     std = fwd["std"] if mode != "none" else torch.ones_like(fwd["nf"])
@@ -67,7 +96,14 @@ def sae_grads(p: Dict[str, torch.Tensor], x: torch.Tensor, fwd: Dict[str, torch.
     acts = fwd["feature_acts"]
     gW_dec = acts.t() @ g
     d_acts = g @ p["W_dec"].t()
-    d_pre = d_acts * (acts > 0)                                           # TopK mask AND ReLU mask
+    if fwd["l1"] is not None:
+        d_acts = d_acts + l1_coefficient / Bt                             # d(l1)/d(acts) where acts > 0 (|a| = a)
+    d_pre = d_acts * (acts > 0)                                           # ReLU mask (AND the TopK support)
+    if dead_mask is not None:                                             # ghost path: only G depends on the parameters
+        E, dG0 = fwd["ghost_E"], fwd["ghost_dG0"]
+        gW_dec[dead_mask] += E.t() @ dG0
+        d_pre = d_pre.clone()
+        d_pre[:, dead_mask] += (dG0 @ p["W_dec"][dead_mask, :].t()) * E
     gW_enc = fwd["sae_in"].t() @ d_pre
     gb_enc = d_pre.sum(0)
     d_sae_in = d_pre @ p["W_enc"].t()
@@ -89,11 +125,13 @@ def new_adam_state(p: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, torch.Tens
 
 def sae_train_step(p: Dict[str, torch.Tensor], state, x: torch.Tensor, k: int, lr: float, t: int, mode: str = "layer_norm",
                    max_grad_norm: Optional[float] = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
-                   since_fired: Optional[torch.Tensor] = None, act_freq: Optional[torch.Tensor] = None):
+                   since_fired: Optional[torch.Tensor] = None, act_freq: Optional[torch.Tensor] = None, act: str = "topk",
+                   l1_coefficient: float = 0.0, use_ghost_grads: bool = False, dead_feature_window: int = 5000):
     """One reference train_step (train_sae.py:278-411), in place on p / state.  t = 1-based optimizer step."""
     p["W_dec"] /= torch.norm(p["W_dec"], dim=1, keepdim=True)             # :307 set_decoder_norm_to_unit_norm
-    fwd = sae_forward(p, x, k, mode)
-    grads = sae_grads(p, x, fwd, mode)
+    dead_mask = (since_fired > dead_feature_window) if (use_ghost_grads and since_fired is not None) else None   # train_sae.py:330-332
+    fwd = sae_forward(p, x, k, mode, act=act, l1_coefficient=l1_coefficient, dead_mask=dead_mask)
+    grads = sae_grads(p, x, fwd, mode, l1_coefficient=l1_coefficient, dead_mask=dead_mask)
     raw_grads = {n: g.clone() for n, g in grads.items()}
     acts = fwd["feature_acts"]
     if since_fired is not None:                                           # :356-361
@@ -118,4 +156,5 @@ def sae_train_step(p: Dict[str, torch.Tensor], state, x: torch.Tensor, k: int, l
         st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
         denom = st["v"].sqrt() / math.sqrt(1 - b2 ** t) + eps
         p[name] -= (lr / (1 - b1 ** t)) * st["m"] / denom
-    return dict(mse=fwd["mse"], l0=l0, grad_norm=total_norm, clip=clip, idx=fwd["idx"], fwd=fwd, grads=grads, raw_grads=raw_grads)
+    return dict(loss=fwd["loss"], l1=fwd["l1"], ghost=fwd["ghost"], n_dead=(0 if dead_mask is None else int(dead_mask.sum())),
+                mse=fwd["mse"], l0=l0, grad_norm=total_norm, clip=clip, idx=fwd["idx"], fwd=fwd, grads=grads, raw_grads=raw_grads)

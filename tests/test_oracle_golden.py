@@ -67,10 +67,11 @@ def _sae_data(gold):
     return torch.randn(n, d, generator=g) * 2.0 + torch.randn(d, generator=g)
 
 
-@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e", "f"])
 def test_sae_oracle_matches_reference_training(tag):
     """Forward, TopK support, closed-form gradients, clipping, projection, Adam and the LR schedule of the oracle
-    against torch autograd + torch.optim.Adam driving the reference's own SAE module for 6 steps."""
+    against torch autograd + torch.optim.Adam driving the reference's own SAE module for 6 steps.
+    d: dense ReLU + L1; e: TopK + ghost grads (112-122 dead features from step 2); f: ReLU + L1 + ghost grads (77 dead)."""
     gold = load_golden(f"sae_tiny_{tag}.pt")
     data = _sae_data(gold)
     p = {k: v.clone() for k, v in gold["init"].items()}
@@ -81,17 +82,29 @@ def test_sae_oracle_matches_reference_training(tag):
         x = data[s * B:(s + 1) * B]
         lr = gold["lr"] * lr_multiplier(s, gold["warm_up_steps"], gold["total_steps"], gold["lr_end"])
         assert abs(lr - rec["lr"]) < 1e-12
-        out = sae_train_step(p, state, x, k, lr, s + 1, mode=gold["norm"], since_fired=since_fired, act_freq=act_freq)
-        assert torch.equal(out["idx"], rec["topk_idx"]), f"step {s}: TopK indices differ"
+        out = sae_train_step(p, state, x, k, lr, s + 1, mode=gold["norm"], since_fired=since_fired, act_freq=act_freq, act=gold["act"],
+                             l1_coefficient=gold["l1_coefficient"], use_ghost_grads=gold["use_ghost_grads"],
+                             dead_feature_window=gold["dead_feature_window"])
+        if gold["act"] == "topk":
+            assert torch.equal(out["idx"], rec["topk_idx"]), f"step {s}: TopK indices differ"
+        else:
+            assert torch.equal(torch.topk(out["fwd"]["hidden_pre"], 4, dim=-1).indices, rec["topk_idx"])
+            assert abs(out["l1"].item() - rec["l1"]) <= 1e-5 * abs(rec["l1"])
+        assert out["n_dead"] == rec["n_dead"]
+        assert abs(out["ghost"].item() - rec["ghost"]) <= 2e-5 * abs(rec["ghost"]) + 1e-12
+        assert abs(out["loss"].item() - rec["loss"]) <= 1e-5 * abs(rec["loss"])
         assert abs(out["mse"].item() - rec["mse"]) <= 1e-5 * abs(rec["mse"])
         assert abs(out["grad_norm"].item() - rec["grad_norm"]) <= 1e-4 * rec["grad_norm"]
         assert abs(out["l0"].item() - rec["l0"]) < 1e-6
         assert_close(out["fwd"]["sae_out"], rec["sae_out"], 1e-5, f"step {s} sae_out")
+        # ghost term: d/dG [c * (G-r)^2/rcn] with c = mse / ((G-r)^2/rcn + 1e-6) divides by elements that can be ~1e-6, so fp32
+        # round-off in (G - r) is amplified; the reference's own fp32 autograd and this closed form agree to ~1e-4 there
+        gtol = 5e-4 if rec["n_dead"] else 2e-5
         if "raw_grads" in rec:
             for n in p:
-                assert_close(out["raw_grads"][n], rec["raw_grads"][n], 2e-5, f"raw grad {n}")
-                assert_close(out["grads"][n], rec["final_grads"][n], 2e-5, f"clipped+projected grad {n}")
+                assert_close(out["raw_grads"][n], rec["raw_grads"][n], gtol, f"step {s} raw grad {n}")
+                assert_close(out["grads"][n], rec["final_grads"][n], gtol, f"step {s} clipped+projected grad {n}")
         if "params_after" in rec:
             for n in p:
-                assert_close(p[n], rec["params_after"][n], 2e-5, f"step {s} param {n}")
+                assert_close(p[n], rec["params_after"][n], 5e-4 if gold["use_ghost_grads"] else 2e-5, f"step {s} param {n}")
     assert torch.equal(since_fired, gold["since_fired"]) and torch.equal(act_freq, gold["act_freq"])

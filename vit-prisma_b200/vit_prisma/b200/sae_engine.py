@@ -187,6 +187,18 @@ class SaeStepEngine:
         return s
 
     # ------------------------------------------------------------------ pieces
+    def _encoder_gemm(self, rows: int) -> None:
+        """hidden_pre = sae_in @ W_enc + b_enc (sae.py:568) on the tcgen05 GEMM (3xTF32) or the exact FFMA kernel."""
+        lib, st = L.get_lib(), _stream()
+        use_tc = self.gemm_impl != L.GEMM_SIMT
+        g = L.PbGemm()
+        g.M, g.N, g.K, g.dtype, g.impl = rows, self.F, self.d, L.PB_F32, self.gemm_impl
+        g.A, g.lda, g.B, g.ldb = self.sae_in.data_ptr(), self.d, self.W_encT.data_ptr(), self.d
+        if use_tc:
+            g.A_lo, g.B_lo = self.sae_in_lo.data_ptr(), self.W_encT_lo.data_ptr()
+        g.bias, g.out0, g.ld0 = self.b_enc.data_ptr(), self.hidden_pre.data_ptr(), self.F
+        L.check(lib.pb_gemm(C.byref(g), st), "pb_gemm(encoder)")
+
     def encode_topk(self, x: torch.Tensor) -> None:
         """prep + encoder GEMM + topk; fills sae_in, mu, sd, xsum, hidden_pre, idx, val, feat_count."""
         lib, st = L.get_lib(), _stream()
@@ -196,13 +208,7 @@ class SaeStepEngine:
         L.check(lib.pb_sae_prep(x.data_ptr(), self.b_dec.data_ptr(), self.sae_in.data_ptr(),
                                 self.sae_in_lo.data_ptr() if use_tc else None, self.mu.data_ptr(), self.sd.data_ptr(),
                                 self.xsum.data_ptr(), rows, self.d, self.norm_mode, st), "pb_sae_prep")
-        g = L.PbGemm()
-        g.M, g.N, g.K, g.dtype, g.impl = rows, self.F, self.d, L.PB_F32, self.gemm_impl
-        g.A, g.lda, g.B, g.ldb = self.sae_in.data_ptr(), self.d, self.W_encT.data_ptr(), self.d
-        if use_tc:
-            g.A_lo, g.B_lo = self.sae_in_lo.data_ptr(), self.W_encT_lo.data_ptr()
-        g.bias, g.out0, g.ld0 = self.b_enc.data_ptr(), self.hidden_pre.data_ptr(), self.F
-        L.check(lib.pb_gemm(C.byref(g), st), "pb_gemm(encoder)")
+        self._encoder_gemm(rows)
         self.feat_count.zero_()
         scratch = self.topk_scratch
         L.check(lib.pb_sae_topk(self.hidden_pre.data_ptr(), rows, self.F, self.k, self.idx.data_ptr(), self.val.data_ptr(),
