@@ -258,6 +258,40 @@ PB_API int pb_sae_mse(const float* x, const float* out, float* xsum_scratch, flo
 /* W[f,:] /= ||W[f,:]|| (set_decoder_norm_to_unit_norm, sae.py:275-277); optional tf32 residual */
 PB_API int pb_unit_norm_rows(float* W, float* W_lo, int32_t F, int32_t d, pb_stream_t stream);
 
+/* ------------------------------------------------ dense SAE step pieces (activation_fn_str = "relu" + L1) and ghost grads
+ * StandardSparseAutoencoder.forward with a dense activation executes six [tokens x d_sae x d_in] products
+ * (sae/sae.py:568, 585 and their autograd transposes); here they run on pb_gemm, these entry points are the glue between
+ * them, and pb_sae_adam finishes the step exactly as in the TopK pipeline.  Ghost grads: sae/sae.py:151-179.          */
+/* out[c][r] = in[r][c] (fp32 [rows][cols] -> [cols][rows]); out_lo (optional) = tf32 residual of the transposed values */
+PB_API int pb_transpose(const float* in, float* out, float* out_lo, int32_t rows, int32_t cols, pb_stream_t stream);
+/* out[c] (+)= sum_r x[r][c]                                    (gb_enc = colsum(d_hidden), sae.py autograd of :568)    */
+PB_API int pb_colsum(const float* x, float* out, int32_t rows, int32_t cols, int32_t accumulate, pb_stream_t stream);
+/* out[c] (+)= sum_f v[f] * W[f][c]                             (sum over tokens of d_hidden @ W_enc^T = gb_enc @ W_enc^T) */
+PB_API int pb_gemv_rows(const float* W, const float* v, float* out, int32_t F, int32_t d, int32_t accumulate, pb_stream_t stream);
+/* fired[f] += #{tokens: acts > 0}; *l1_sum += sum |acts|; scalars.pos_count += #{acts > 0}  (train_sae.py:356-365, sae.py:617) */
+PB_API int pb_sae_dense_stats(const float* acts, int32_t rows, int32_t F, float* fired, float* l1_sum, void* scalars, pb_stream_t stream);
+/* sae_out = norm_out(out_n); scalars.loss_sum += sum (sae_out-x)^2/||x - mean_batch x||; g = dL/d out_n; resid = x - sae_out
+ * (sae.py:144-149, 584-595); sae_out / g / resid may be NULL; xsum = column sums of x over the GLOBAL batch of global_rows tokens */
+PB_API int pb_sae_dense_loss(const float* x, const float* out_n, const float* mu, const float* sd, const float* xsum, float* sae_out,
+                             float* g, float* resid, void* scalars, int32_t rows, int32_t global_rows, int32_t d, int32_t norm_mode,
+                             pb_stream_t stream);
+/* d_hidden = (d_acts + l1_grad) * [acts > 0] in place on d_acts (+ optional tf32 residual): ReLU backward with d(l1)/d(acts) */
+PB_API int pb_sae_dense_dhid(float* d_acts, const float* acts, float* lo, float l1_grad, int64_t n, pb_stream_t stream);
+/* scalars: gnorm_sq = ||all four gradients||^2, grad_norm, clip_coef (train_sae.py:394-397), mse, l0 -- then pb_sae_adam */
+PB_API int pb_sae_grad_finish(const float* gW_dec, const float* gW_encT, const float* gb_enc, const float* gb_dec, int32_t F, int32_t d,
+                              void* scalars, float max_grad_norm, int32_t rows, pb_stream_t stream);
+/* E[r][j] = exp(hidden_pre[r][dead_idx[j]]), zero for nd <= j < ldE                                   (sae.py:164)  */
+PB_API int pb_sae_ghost_gather(const float* hidden_pre, const int32_t* dead_idx, int32_t nd, int32_t rows, int32_t F, float* E, int32_t ldE,
+                               pb_stream_t stream);
+/* out[j] = W[idx[j]] (j < n), zero rows up to n_pad;   dst[idx[j]] += scale * src[j] (distinct indices)                */
+PB_API int pb_gather_rows(const float* W, const int32_t* idx, int32_t n, int32_t n_pad, int32_t d, float* out, pb_stream_t stream);
+PB_API int pb_scatter_add_rows(float* dst, const int32_t* idx, int32_t n, int32_t d, const float* src, float scale, pb_stream_t stream);
+PB_API int pb_mul_inplace(float* y, const float* x, int64_t n, pb_stream_t stream);
+/* per token row: rescale G0 = exp(h_dead) @ W_dec[dead] to half the residual norm, ghost_sum += sum c*(G-r)^2/rcn with
+ * c = mse/((G-r)^2/rcn + 1e-6), and overwrite G0 with dL_ghost/dG0 (sae.py:157-178); rsum = column sums of resid            */
+PB_API int pb_sae_ghost_rows(const float* resid, const float* rsum, float* G0, const void* scalars, float* ghost_sum, int32_t rows,
+                             int32_t d, pb_stream_t stream);
+
 /* ------------------------------------------------ data-parallel SAE step over NVLink peer memory
  * New functionality (the reference trains on one device): gradients are reduce-scattered by direct peer loads,
  * the owner of a feature-row slice runs clip + projection + Adam + renorm and stores the new rows into every peer

@@ -34,15 +34,13 @@ __device__ __forceinline__ void mma_tf32x3(float (&d)[4], const float (&a)[4], c
   uint32_t ah[4], al[4], bh[2], bl[2];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float hi = tf32_trunc(a[i]);
-    ah[i] = __float_as_uint(hi);
-    al[i] = __float_as_uint(a[i] - hi);
+    ah[i] = __float_as_uint(a[i]);            // mma.sync reads the tf32 part of the word
+    al[i] = __float_as_uint(tf32_lo(a[i]));
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const float hi = tf32_trunc(b[i]);
-    bh[i] = __float_as_uint(hi);
-    bl[i] = __float_as_uint(b[i] - hi);
+    bh[i] = __float_as_uint(b[i]);
+    bl[i] = __float_as_uint(tf32_lo(b[i]));
   }
   mma_tf32(d, al, bh);
   mma_tf32(d, ah, bl);

@@ -88,6 +88,14 @@ __device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
 __device__ __forceinline__ float tf32_trunc(float x) {
   return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
+// low plane of the 3xTF32 split: x - hi, itself rounded to the NEAREST tf32 so that the tensor core's truncating read of the
+// plane is exact.  A truncated lo loses up to 2^-20 |x| per element, always in the same direction, so the error of a K-term dot
+// product grows like K (measured 2.6e-5 at K = 3072); rounded, it is +-2^-21 |x| and averages out (profiles/r01_gemm_notes.md).
+__device__ __forceinline__ float tf32_lo(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x - tf32_trunc(x)));
+  return __uint_as_float(r);
+}
 
 // ------------------------------------------------------------- activations
 // Matches torch: F.gelu (erf), F.silu, F.relu and the closed forms in

@@ -159,12 +159,12 @@ __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ x,
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = reinterpret_cast<const float4*>(x)[i];
-    float4 r = make_float4(v.x - tf32_trunc(v.x), v.y - tf32_trunc(v.y), v.z - tf32_trunc(v.z), v.w - tf32_trunc(v.w));
+    float4 r = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
     reinterpret_cast<float4*>(lo)[i] = r;
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     int64_t i = (n4 << 2) + threadIdx.x;
-    lo[i] = x[i] - tf32_trunc(x[i]);
+    lo[i] = tf32_lo(x[i]);
   }
 }
 extern "C" int pb_split_tf32(const float* x, float* lo, int64_t n, pb_stream_t s) {

@@ -57,7 +57,7 @@ __device__ __forceinline__ void epilogue_store4(const EpiParams& ep, int row, in
       if (ep.out1_lo) {
         float l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) l[j] = o[j] - tf32_trunc(o[j]);
+        for (int j = 0; j < 4; ++j) l[j] = tf32_lo(o[j]);
         st4(ep.out1_lo + (int64_t)row * ep.ld1 + col, l);
       }
     }
@@ -76,7 +76,7 @@ __device__ __forceinline__ void epilogue_store4(const EpiParams& ep, int row, in
       if (ep.out1) {
         const float o = ep.residual ? ld_as_float((const T*)ep.residual + (int64_t)row * ep.ldr + c) + v : apply_act(v, ep.act);
         st_from_float((T*)ep.out1 + (int64_t)row * ep.ld1 + c, o);
-        if (ep.out1_lo) ep.out1_lo[(int64_t)row * ep.ld1 + c] = o - tf32_trunc(o);
+        if (ep.out1_lo) ep.out1_lo[(int64_t)row * ep.ld1 + c] = tf32_lo(o);
       }
     }
   }

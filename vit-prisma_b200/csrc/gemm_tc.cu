@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const __grid_constant__ 
             else o = apply_act(v, ep.act);
             st_from_float(o1, o);
             o1 += ep.ld1;
-            if (o1lo) { *o1lo = o - tf32_trunc(o); o1lo += ep.ld1; }
+            if (o1lo) { *o1lo = tf32_lo(o); o1lo += ep.ld1; }
           }
         }
       }
@@ -328,7 +328,7 @@ __device__ __forceinline__ void epi_rows_scalar(const EpiParams& ep, const float
       else o = apply_act(v, ep.act);
       st_from_float(o1, o);
       o1 += ep.ld1;
-      if (o1lo) { *o1lo = o - tf32_trunc(o); o1lo += ep.ld1; }
+      if (o1lo) { *o1lo = tf32_lo(o); o1lo += ep.ld1; }
     }
   }
 }
@@ -384,7 +384,7 @@ __device__ __forceinline__ void epi_pair_loop(const float* __restrict__ stage, i
       else { x0 = apply_act(v0, act); x1 = apply_act(v1, act); }
       st2(o1, x0, x1);
       o1 += 2 * ld1;
-      if (o1lo) { st2(o1lo, x0 - tf32_trunc(x0), x1 - tf32_trunc(x1)); o1lo += 2 * ld1; }
+      if (o1lo) { st2(o1lo, tf32_lo(x0), tf32_lo(x1)); o1lo += 2 * ld1; }
     }
   }
 }
@@ -554,7 +554,7 @@ __device__ __forceinline__ void epi_chunk_vec(const EpiParams& ep, const uint32_
   __syncwarp();
   if (sizeof(T) == 4 && ep.out1_lo) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = v[j] - tf32_trunc(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = tf32_lo(v[j]);
     stage_put_row(my_row, v, T());
     __syncwarp();
     stage_copy_out<T>(stage, (T*)ep.out1_lo + (int64_t)row0 * ep.ld1 + col0, ep.ld1, lane, nrows);

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_layernorm_reg(const TI* __restrict__ x,
       if (out_lo) {
         float l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) l[j] = y[j] - tf32_trunc(y[j]);
+        for (int j = 0; j < 4; ++j) l[j] = tf32_lo(y[j]);
         st4(out_lo + o, l);
       }
     }
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_layernorm_generic(const TI* __restrict_
     const int64_t o = row * cols + c;
     if (norm_f32) norm_f32[o] = y;
     if (out) st_from_float(out + o, y);
-    if (out_lo) out_lo[o] = y - tf32_trunc(y);
+    if (out_lo) out_lo[o] = tf32_lo(y);
   }
 }
 

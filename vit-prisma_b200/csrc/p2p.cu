@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           p[q] = adam_upd(p[q], gr[q] * clip, mm[q], vv[q], h);
-          lo[q] = p[q] - tf32_trunc(p[q]);
+          lo[q] = tf32_lo(p[q]);
         }
         st4(m_enc + base + 4 * c4, mm);
         st4(v_enc + base + 4 * c4, vv);

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_sae_prep(const float* __restrict__ x, c
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         o[j] = (norm_mode == 1 ? v[i][j] / (sd + eps) : v[i][j] * inv) - bd[j];
-        lo[j] = o[j] - tf32_trunc(o[j]);
+        lo[j] = tf32_lo(o[j]);
       }
       (void)inv;
       st4(sae_in + (int64_t)row * d + 4 * c4, o);
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           p[q] = adam_update(p[q], gr[q] * clip, mm[q], vv[q], h);
-          lo[q] = p[q] - tf32_trunc(p[q]);
+          lo[q] = tf32_lo(p[q]);
         }
         st4(W_encT + base + 4 * c4, p);
         st4(m_enc + base + 4 * c4, mm);
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(256) k_unit_rows(float* __restrict__ W, float*
       if (c4 < nvec) {
         float lo[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { w[i][q] = w[i][q] / nrm; lo[q] = w[i][q] - tf32_trunc(w[i][q]); }
+        for (int q = 0; q < 4; ++q) { w[i][q] = w[i][q] / nrm; lo[q] = tf32_lo(w[i][q]); }
         st4(W + (int64_t)f * d + 4 * c4, w[i]);
         if (W_lo) st4(W_lo + (int64_t)f * d + 4 * c4, lo);
       }

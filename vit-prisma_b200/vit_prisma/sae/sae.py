@@ -227,16 +227,27 @@ class StandardSparseAutoencoder(SparseAutoencoder):
         return self.W_enc.data.t(), self.W_dec.data, self.b_enc.data, self.b_dec.data
 
     def step_engine(self, gemm_impl: int = L.GEMM_AUTO):
-        """The fused TopK engine bound to this module's parameter storage (rebuilt if the storage moved)."""
+        """The step engine bound to this module's parameter storage (rebuilt if the storage moved): the fused sparse TopK
+        pipeline, or ``SaeDenseStepEngine`` for ``activation_fn_str == "relu"`` (dense products + L1) and for
+        ``cfg.use_ghost_grads`` with either activation (vit_prisma/b200/sae_dense.py)."""
         from vit_prisma.b200.sae_engine import SaeStepEngine
-        if self.cfg.activation_fn_str != "topk":
-            raise NotImplementedError("the fused step engine covers activation_fn_str == 'topk'")
+        act = self.cfg.activation_fn_str
+        if act not in ("topk", "relu"):
+            raise NotImplementedError(f"B200 training step: activation_fn_str {act!r} is not built (topk and relu are)")
+        if act == "relu" and getattr(self.cfg, "lp_norm", 1) != 1:
+            raise NotImplementedError("B200 dense training step: only lp_norm == 1 (the reference default) is built")
+        dense = act == "relu" or bool(self.cfg.use_ghost_grads)
         wt, wd, be, bd = self._canonical_params()
         eng = self._engine
-        key = (wt.data_ptr(), wd.data_ptr(), be.data_ptr(), bd.data_ptr(), gemm_impl)
+        key = (wt.data_ptr(), wd.data_ptr(), be.data_ptr(), bd.data_ptr(), gemm_impl, dense)
         if eng is None or eng._key != key:
-            eng = SaeStepEngine(wt, wd, be, bd, k=self.cfg.activation_fn_kwargs["k"], normalize_activations=self._norm_mode,
-                                max_grad_norm=self.cfg.max_grad_norm, gemm_impl=gemm_impl)
+            k = self.cfg.activation_fn_kwargs["k"] if act == "topk" else 1
+            kw = dict(k=k, normalize_activations=self._norm_mode, max_grad_norm=self.cfg.max_grad_norm, gemm_impl=gemm_impl)
+            if dense:
+                from vit_prisma.b200.sae_dense import SaeDenseStepEngine
+                eng = SaeDenseStepEngine(wt, wd, be, bd, l1_coefficient=self.cfg.l1_coefficient, **kw)
+            else:
+                eng = SaeStepEngine(wt, wd, be, bd, **kw)
             eng._key = key
             eng._enc_version = self.W_enc._version
             self._engine = eng
@@ -298,9 +309,8 @@ class StandardSparseAutoencoder(SparseAutoencoder):
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, x: torch.Tensor, dead_neuron_mask: torch.Tensor = None, *args, **kwargs):
-        if self.cfg.use_ghost_grads and self.training and dead_neuron_mask is not None and bool(dead_neuron_mask.any()):
-            raise NotImplementedError("ghost-grad auxiliary loss is not built on the B200 path yet (SURVEY 8a b8)")
         from vit_prisma.b200.sae_engine import sae_mse
+        want_ghost = bool(self.cfg.use_ghost_grads) and self.training and dead_neuron_mask is not None   # (:609-614)
         lead = x.shape[:-1]
         x32 = ops.cast(x, self.dtype) if x.dtype != self.dtype else x
         x2 = x32.reshape(-1, self.d_in).contiguous()
@@ -316,21 +326,28 @@ class StandardSparseAutoencoder(SparseAutoencoder):
             if getattr(self.cfg, "return_out_only", False):
                 return sae_out
             feature_acts = eng.dense_feature_acts().view(*lead, self.d_sae)
+            hidden_pre2 = eng.hidden_pre
         else:
             _, feature_acts, _hidden_pre = self.encode(x32, return_hidden_pre=True)
             sae_out = self.decode(feature_acts)
             if getattr(self.cfg, "return_out_only", False):
                 return sae_out
             mse_loss = sae_mse(x2, sae_out.reshape(-1, self.d_in).contiguous())
+            hidden_pre2 = _hidden_pre.reshape(-1, self.d_sae)
+        ghost_loss = self.zero_loss.to(sae_out.device)
+        if want_ghost:
+            from vit_prisma.b200.sae_dense import ghost_loss_value
+            ghost_loss = ghost_loss_value(hidden_pre2.float().contiguous(), self._canonical_params()[1], x2.float(),
+                                          sae_out.reshape(-1, self.d_in).float().contiguous(), mse_loss.float(), dead_neuron_mask)
         if self.cfg.activation_fn_str != "topk":
             # sparsity = ||feature_acts||_p over dim 1, mean over dim 0 (reference :617; tiny reduction, host-side glue)
             sparsity = feature_acts.norm(p=self.lp_norm, dim=1).mean(dim=(0,))
             l1_loss = self.l1_coefficient * sparsity
-            loss = mse_loss + l1_loss
+            loss = mse_loss + l1_loss + ghost_loss
         else:
             l1_loss = None
-            loss = mse_loss.clone()
-        return (sae_out, feature_acts, loss, mse_loss, l1_loss, self.zero_loss.to(sae_out.device), torch.tensor(0.0))
+            loss = mse_loss + ghost_loss
+        return (sae_out, feature_acts, loss, mse_loss, l1_loss, ghost_loss, torch.tensor(0.0))
 
 
 class GatedSparseAutoencoder(SparseAutoencoder):

@@ -175,10 +175,23 @@ class VisionSAETrainer:
             n_frac_active_tokens = 0
 
         lr = optimizer.param_groups[0]["lr"]
-        scalars = engine.train_step(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores)
+        l1_loss = None
+        if cfg.activation_fn_str == "relu":                          # dense products + L1 (+ ghost grads), sae_dense.py
+            scalars = engine.train_step_dense(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores,
+                                              use_ghost_grads=bool(cfg.use_ghost_grads), dead_feature_window=cfg.dead_feature_window)
+        elif cfg.use_ghost_grads:                                    # sparse TopK gradients + ghost blocks on the dead features
+            scalars = engine.train_step_topk_ghost(sae_in, lr, n_forward_passes_since_fired, act_freq_scores, cfg.dead_feature_window)
+        else:
+            scalars = engine.train_step(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores)
         n_frac_active_tokens += sae_in.shape[0]
         mse_loss = scalars[3]
         loss = mse_loss            # TopK: loss == mse (no L1 term, train_sae.py:617-626)
+        if hasattr(engine, "aux"):                                   # device-side: loss = mse + l1 + ghost (sae.py:628)
+            ghost_loss = engine.aux[1] / float(sae_in.shape[0] * engine.d)
+            if cfg.activation_fn_str != "topk":
+                l1_loss = engine.aux[0] * (engine.l1_coefficient / sae_in.shape[0])
+                loss = loss + l1_loss
+            loss = loss + ghost_loss
         l0 = scalars[4]
         if self.cfg.log_to_wandb and (n_training_steps + 1) % self.cfg.wandb_log_frequency == 0:
             vals = engine.scalars_dict()
@@ -189,7 +202,7 @@ class VisionSAETrainer:
                        "sparsity/dead_features": (n_forward_passes_since_fired > cfg.dead_feature_window).sum().item()},
                       n_training_steps)
         scheduler.step()
-        return loss, mse_loss, None, l0, act_freq_scores, n_forward_passes_since_fired, n_frac_active_tokens
+        return loss, mse_loss, l1_loss, l0, act_freq_scores, n_forward_passes_since_fired, n_frac_active_tokens
 
     # ------------------------------------------------------------------ logging / checkpoints
     def initalize_wandb(self):
