@@ -119,24 +119,30 @@ def _cpu_cores():
 
 
 # ------------------------------------------------------------------ CPU (oracle port) arm
-def cpu_vit_images_per_sec(budget_s=12.0, batch=16, threads=None):
+def cpu_vit_images_per_sec(budget_s=12.0, batch=16, threads=None, cfg=None, layer=None):
+    """Oracle port on the host cores; ``layer`` = the activation-store call (names_filter one resid_post + stop_at_layer)."""
     from oracle.vit_oracle import CLIP_B32, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
     threads = threads or _cpu_cores()
     torch.set_num_threads(threads)
-    cfg = dict(CLIP_B32)
+    cfg = dict(cfg or CLIP_B32)
+    kw = {}
+    if layer is not None:
+        name = f"blocks.{layer}.hook_resid_post"
+        kw = dict(names_filter=lambda n: n == name, stop_at_layer=layer + 1)
     sd = recipe_state_dict(state_dict_shapes(cfg), 1234)
     x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
-        vit_forward_with_cache(sd, cfg, x)  # warm-up
+        vit_forward_with_cache(sd, cfg, x, **kw)  # warm-up
         n, t0 = 0, time.perf_counter()
         while True:
-            vit_forward_with_cache(sd, cfg, x)
+            vit_forward_with_cache(sd, cfg, x, **kw)
             n += 1
             dt = time.perf_counter() - t0
             if dt >= budget_s or n >= 64:
                 break
+    what = f"resid_post of layer {layer}, stop_at_layer {layer + 1}" if layer is not None else "all default hook points"
     return {"value": n * batch / dt, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"{n} x run_with_cache(batch {batch}) CLIP ViT-B/32 fp32, all 214 hook points, oracle/vit_oracle.py, {dt:.1f}s"}
+            "sample": f"{n} x run_with_cache(batch {batch}) d_model {cfg['d_model']} x {cfg['n_layers']} layers fp32, {what}, oracle/vit_oracle.py, {dt:.1f}s"}
 
 
 def run_reference_arm(args):
@@ -170,24 +176,28 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------ GPU arm
-def build_model(dtype, device):
+def build_model(dtype, device, cfg=None):
     from oracle.vit_oracle import CLIP_B32, recipe_state_dict
     from vit_prisma.configs.HookedViTConfig import HookedViTConfig
     from vit_prisma.models.base_vit import HookedViT
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
-        model = HookedViT(HookedViTConfig(**CLIP_B32, dtype=dtype))
+        model = HookedViT(HookedViTConfig(**(cfg or CLIP_B32), dtype=dtype))
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     model.load_state_dict(recipe_state_dict(shapes, 1234))
     return model.to(device, dtype).eval()
 
 
-def vit_flops_per_image(cfg):
+def vit_flops_per_image(cfg, stop_at_layer=None):
+    """full depth, or L = stop_at_layer without the head term."""
     N = (cfg["image_size"] // cfg["patch_size"]) ** 2
     T = N + 1
     d, H, dh, M, L = cfg["d_model"], cfg["n_heads"], cfg["d_head"], cfg["d_mlp"], cfg["n_layers"]
     CPP = cfg["n_channels"] * cfg["patch_size"] ** 2
-    return 2 * N * CPP * d + L * (6 * T * d * H * dh + 4 * H * T * T * dh + 2 * T * H * dh * d + 4 * T * d * M) + 2 * d * cfg["n_classes"]
+    head = 2 * d * cfg["n_classes"]
+    if stop_at_layer is not None:
+        L, head = stop_at_layer, 0
+    return 2 * N * CPP * d + L * (6 * T * d * H * dh + 4 * H * T * T * dh + 2 * T * H * dh * d + 4 * T * d * M) + head
 
 
 def time_dominant_gemm(model, batch, dtype, iters=10):
@@ -225,10 +235,14 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from oracle.vit_oracle import CLIP_B32
+    from oracle.vit_oracle import CLIP_B32, CLIP_L14
     from vit_prisma.b200 import _lib as L
     dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
-    model = build_model(dtype, dev)
+    l14 = args.model == "l14"
+    CFG = CLIP_L14 if l14 else CLIP_B32
+    # cfg #4 (ViT part): exactly the call VisionActivationsStore.get_activations makes (activations_store.py:262-270)
+    run_kw = dict(names_filter=[f"blocks.{args.layer}.hook_resid_post"], stop_at_layer=args.layer + 1) if l14 else {}
+    model = build_model(dtype, dev, CFG)
     B = args.batch
     g = torch.Generator().manual_seed(rank)
     host = torch.randn(B, 3, 224, 224, generator=g).to(dtype).pin_memory()
@@ -253,7 +267,7 @@ def run_ours(args):
     # ---- device-resident throughput
     clocks = ClockSampler(local)
     for _ in range(args.warmup):
-        out, cache = model.run_with_cache(x)
+        out, cache = model.run_with_cache(x, **run_kw)
         del cache
     barrier()
     n_keys = 0
@@ -262,7 +276,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            out, cache = model.run_with_cache(x)
+            out, cache = model.run_with_cache(x, **run_kw)
             n_keys = len(cache)
             del cache
         e1.record()
@@ -273,22 +287,25 @@ def run_ours(args):
     route = model.last_route
 
     # ---- end to end: pinned host batch -> H2D -> run_with_cache -> D2H of the model output, every step
-    out_host = torch.empty((B, CLIP_B32["n_classes"]), dtype=dtype).pin_memory()
+    # result read back every step: the model output [B, n_classes]; with stop_at_layer the output is the residual stream
+    # (stays on the device for the SAE), so the class-token row of every image [B, d_model] is what crosses PCIe
+    out_host = torch.empty((B, CFG["d_model"] if l14 else CFG["n_classes"]), dtype=dtype).pin_memory()
+    result = (lambda o: o[:, 0, :]) if l14 else (lambda o: o)
     # (the copy of batch i+1 runs on a side stream under batch i's forward -- vit_prisma.b200.prefetch.DevicePrefetcher, the
     # loader-side helper the package ships; every step's bytes still cross PCIe inside the timed region)
     from vit_prisma.b200.prefetch import DevicePrefetcher
     loader = DevicePrefetcher(None, dev)         # built once, like a DataLoader: the timed region holds per-step work only
     for xd in loader.feed(host for _ in range(max(3, args.warmup))):
-        out, cache = model.run_with_cache(xd)
-        out_host.copy_(out, non_blocking=True)
+        out, cache = model.run_with_cache(xd, **run_kw)
+        out_host.copy_(result(out), non_blocking=True)
         del cache
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     marks = []
     for xd in loader.feed(host for _ in range(args.steps)):
-        out, cache = model.run_with_cache(xd)
-        out_host.copy_(out, non_blocking=True)
+        out, cache = model.run_with_cache(xd, **run_kw)
+        out_host.copy_(result(out), non_blocking=True)
         del cache
         if os.environ.get("PRISMA_BENCH_DEBUG"):
             marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
@@ -306,12 +323,13 @@ def run_ours(args):
     value = imgs / (dev_ms / 1e3)
     e2e = imgs / (e2e_ms / 1e3)
     kern = time_dominant_gemm(model, B, dtype)
-    flops_img = vit_flops_per_image(CLIP_B32)
+    flops_img = vit_flops_per_image(CFG, run_kw.get("stop_at_layer"))
+    cache_b_img = (CFG["d_model"] * ((CFG["image_size"] // CFG["patch_size"]) ** 2 + 1) * 4) if l14 else 38_980_176   # fp32 bytes
     # fp32 mode executes 3 tensor-core passes per algorithmic flop; the roofline counts ALGORITHMIC flops
     achieved = kern["flops"] / (kern["ms"] / 1e3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from one `ncu --set full` capture (profiles/r01_gemm_fp32_ncu_summary.txt,
     # profiles/r01_gemm_bf16_v3_ncu_summary.txt); algorithmic: A (+ lo plane) + weights read, two M x N outputs written
-    traffic = (180.070400e6 + 580.768512e6) if dtype == torch.float32 else (44.133632e6 + 262.480640e6)
+    traffic = None if l14 else ((180.070400e6 + 580.768512e6) if dtype == torch.float32 else (44.133632e6 + 262.480640e6))
     roof = {"bound": "tensor", "kernel": "k_gemm_tc2 (MLP-in GEMM + bias + GELU, hook_pre/hook_post spill)", "achieved": achieved,
             "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
             "traffic_unit": "B/launch (ncu dram read+write)", "algorithmic_bytes": kern["bytes"],
@@ -323,16 +341,19 @@ def run_ours(args):
             "hbm_gbs_of_kernel": kern["bytes"] / (kern["ms"] / 1e3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
             "passes": 3 if dtype == torch.float32 else 1,
             "step_algorithmic_tflops": flops_img * imgs / (dev_ms / 1e3) / 1e12,
-            "step_cache_write_gbs": 38_980_176 * (1 if dtype == torch.float32 else 0.5) * imgs / (dev_ms / 1e3) / 1e9}
-    cpu = cpu_vit_images_per_sec()
+            "step_cache_write_gbs": cache_b_img * (1 if dtype == torch.float32 else 0.5) * imgs / (dev_ms / 1e3) / 1e9}
+    cpu = cpu_vit_images_per_sec(batch=4, cfg=CFG, layer=args.layer) if l14 else cpu_vit_images_per_sec()
     es = 4 if dtype == torch.float32 else 2
-    line = {"metric": "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)", "value": value, "unit": "images/s",
+    metric = (f"run_with_cache images/sec (CLIP ViT-L/14, blocks.{args.layer}.hook_resid_post, stop_at_layer={args.layer + 1})" if l14
+              else "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)")
+    line = {"metric": metric, "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "vit_b32_run_with_cache_all_hooks", "model": "CLIP ViT-B/32 geometry, seeded synthetic weights",
+            "config": {"workload": f"vit_l14_run_with_cache_resid_post_l{args.layer}" if l14 else "vit_b32_run_with_cache_all_hooks",
+                       "model": ("CLIP ViT-L/14" if l14 else "CLIP ViT-B/32") + " geometry, seeded synthetic weights",
                        "batch_per_gpu": B, "global_batch": B * world, "hook_points_cached": n_keys, "route": route,
                        "gemm": "tcgen05 3xTF32" if dtype == torch.float32 else "tcgen05 bf16",
-                       "cache_bytes_per_image": int(38_980_176 * es / 4), "l2": "working set (cache arena >> 126 MB) larger than L2",
+                       "cache_bytes_per_image": int(cache_b_img * es / 4), "l2": "working set (activations of one layer >> 126 MB) larger than L2",
                        "parallelism": f"dp{world} (images sharded, no collective)"},
             "clocks": clocks.summary(), "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * host.element_size()),
@@ -531,14 +552,22 @@ def main():
     ap.add_argument("--workload", default="vit", choices=["vit", "sae"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--model", default="b32", choices=["b32", "l14"], help="l14 = cfg #4: ViT-L/14 with the activation store's names_filter / stop_at_layer")
+    ap.add_argument("--layer", type=int, default=22, help="hook_resid_post layer cached by --model l14")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
-    if args.workload == "sae":
-        return run_sae(args)
-    run_ours(args)
+    try:
+        if args.workload == "sae":
+            return run_sae(args)
+        run_ours(args)
+    finally:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
