@@ -158,3 +158,73 @@ def sae_train_step(p: Dict[str, torch.Tensor], state, x: torch.Tensor, k: int, l
         p[name] -= (lr / (1 - b1 ** t)) * st["m"] / denom
     return dict(loss=fwd["loss"], l1=fwd["l1"], ghost=fwd["ghost"], n_dead=(0 if dead_mask is None else int(dead_mask.sum())),
                 mse=fwd["mse"], l0=l0, grad_norm=total_norm, clip=clip, idx=fwd["idx"], fwd=fwd, grads=grads, raw_grads=raw_grads)
+
+
+# ------------------------------------------------------------------------------------------------ Gated SAE (sae/sae.py:648-792)
+GATED_PARAMS = ("W_enc", "b_gate", "r_mag", "b_mag", "W_dec", "b_dec")     # b_enc exists in the module but never enters the graph
+
+
+def gated_forward_grads(p: Dict[str, torch.Tensor], x: torch.Tensor, mode: str, l1_coefficient: float):
+    """GatedSparseAutoencoder.forward (ReLU activation) and the closed-form gradients of loss = mse + l1 + aux.
+    The magnitude path shares the encoder: sae_in @ (W_enc * exp(r_mag)) + b_mag = (pi - b_gate) * exp(r_mag) + b_mag."""
+    Bt, d = x.shape
+    xn, mu, std = normalise_in(x, mode)
+    sae_in = xn - p["b_dec"]                                              # :698
+    u = sae_in @ p["W_enc"]
+    pi = u + p["b_gate"]                                                  # :701 gating pre-activation
+    active = (pi > 0).to(x.dtype)                                         # :702 (no gradient)
+    er = p["r_mag"].exp()
+    mag_pre = u * er + p["b_mag"]                                         # :705
+    acts = active * torch.relu(mag_pre)                                   # :707-709
+    out_n = acts @ p["W_dec"] + p["b_dec"]                                # :713-722
+    sae_out = out_n * std + mu if mode == "layer_norm" else (out_n * std if mode == "constant_norm_rescale" else out_n)
+    nf = torch.norm(x - x.mean(dim=0, keepdim=True), p=2, dim=-1, keepdim=True)
+    mse = (((sae_out - x) ** 2) / nf).mean()                              # :144-149
+    pi_act = torch.relu(pi)                                               # :769-774
+    wnorm = p["W_dec"].norm(dim=1)
+    l1 = l1_coefficient * (pi_act * wnorm).sum(-1).mean()                 # :776-781
+    via = pi_act @ p["W_dec"] + p["b_dec"]                                # :786-787
+    aux = ((via - sae_in) ** 2).sum(-1).mean()                            # :788
+    # ---- backward
+    sd = std if mode != "none" else torch.ones_like(nf)
+    g = 2.0 * (sae_out - x) * sd / (nf * Bt * d)                          # d mse / d out_n
+    ga = 2.0 * (via - sae_in) / Bt                                        # d aux / d via  (= - d aux / d sae_in)
+    gW_dec = acts.t() @ g + pi_act.t() @ ga + (l1_coefficient / Bt) * pi_act.sum(0)[:, None] * p["W_dec"] / wnorm[:, None]
+    d_mag = (g @ p["W_dec"].t()) * active * (mag_pre > 0)
+    d_pi = (ga @ p["W_dec"].t() + (l1_coefficient / Bt) * wnorm) * (pi > 0)
+    D = d_pi + d_mag * er                                                 # d loss / d (sae_in @ W_enc)
+    grads = dict(W_enc=sae_in.t() @ D, b_gate=d_pi.sum(0), b_mag=d_mag.sum(0), r_mag=(d_mag * u * er).sum(0), W_dec=gW_dec,
+                 b_dec=g.sum(0) + 2.0 * ga.sum(0) - (D @ p["W_enc"].t()).sum(0))
+    return dict(sae_out=sae_out, feature_acts=acts, mse=mse, l1=l1, aux=aux, loss=mse + l1 + aux, grads=grads)
+
+
+def gated_train_step(p: Dict[str, torch.Tensor], state, x: torch.Tensor, lr: float, t: int, mode: str, l1_coefficient: float,
+                     max_grad_norm: Optional[float] = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                     since_fired: Optional[torch.Tensor] = None, act_freq: Optional[torch.Tensor] = None):
+    """One reference train_step with architecture="gated" (train_sae.py:278-411), in place on p / state (keys GATED_PARAMS)."""
+    p["W_dec"] /= torch.norm(p["W_dec"], dim=1, keepdim=True)
+    out = gated_forward_grads(p, x, mode, l1_coefficient)
+    grads = out["grads"]
+    raw = {n: g.clone() for n, g in grads.items()}
+    acts = out["feature_acts"]
+    if since_fired is not None:
+        did_fire = (acts > 0).float().sum(-2) > 0
+        since_fired += 1
+        since_fired[did_fire] = 0
+    if act_freq is not None:
+        act_freq += (acts.abs() > 0).float().sum(0)
+    total_norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+    clip = 1.0
+    if max_grad_norm:
+        clip = min(1.0, max_grad_norm / (total_norm.item() + 1e-6))
+        for g in grads.values():
+            g *= clip
+    grads["W_dec"] = grads["W_dec"] - (grads["W_dec"] * p["W_dec"]).sum(1, keepdim=True) * p["W_dec"]
+    b1, b2 = betas
+    for name in GATED_PARAMS:
+        st, g = state[name], grads[name]
+        st["m"].mul_(b1).add_(g, alpha=1 - b1)
+        st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+        p[name] -= (lr / (1 - b1 ** t)) * st["m"] / (st["v"].sqrt() / math.sqrt(1 - b2 ** t) + eps)
+    out.update(raw_grads=raw, grad_norm=total_norm, clip=clip, l0=(acts > 0).float().sum(-1).mean())
+    return out

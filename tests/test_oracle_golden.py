@@ -108,3 +108,36 @@ def test_sae_oracle_matches_reference_training(tag):
             for n in p:
                 assert_close(p[n], rec["params_after"][n], 5e-4 if gold["use_ghost_grads"] else 2e-5, f"step {s} param {n}")
     assert torch.equal(since_fired, gold["since_fired"]) and torch.equal(act_freq, gold["act_freq"])
+
+
+@pytest.mark.parametrize("tag", ["g", "h"])
+def test_gated_sae_oracle_matches_reference_training(tag):
+    """GatedSparseAutoencoder (sae.py:648-792) for 6 steps under autograd + torch.optim.Adam vs the closed-form oracle:
+    loss terms, all six parameter gradients (b_enc never enters the graph: grad None in the reference), parameters, counters."""
+    from oracle.sae_oracle import GATED_PARAMS, gated_train_step
+    gold = load_golden(f"sae_gated_{tag}.pt")
+    g = torch.Generator().manual_seed(gold["data_seed"])
+    n, d = gold["batch"] * gold["n_steps"], gold["d_in"]
+    data = torch.randn(n, d, generator=g) * 2.0 + torch.randn(d, generator=g)
+    p = {k: gold["init"][k].clone() for k in GATED_PARAMS}
+    state = new_adam_state(p)
+    since_fired, act_freq = torch.zeros(gold["d_sae"]), torch.zeros(gold["d_sae"])
+    B = gold["batch"]
+    for s, rec in enumerate(gold["steps"]):
+        x = data[s * B:(s + 1) * B]
+        lr = gold["lr"] * lr_multiplier(s, gold["warm_up_steps"], gold["total_steps"], gold["lr_end"])
+        out = gated_train_step(p, state, x, lr, s + 1, gold["norm"], gold["l1_coefficient"], since_fired=since_fired, act_freq=act_freq)
+        for name in ("loss", "mse", "l1", "aux"):
+            assert abs(out[name].item() - rec[name]) <= 2e-5 * abs(rec[name]), (s, name, out[name].item(), rec[name])
+        assert abs(out["grad_norm"].item() - rec["grad_norm"]) <= 1e-4 * rec["grad_norm"]
+        assert_close(out["sae_out"], rec["sae_out"], 1e-5, f"step {s} sae_out")
+        assert torch.equal(out["feature_acts"] > 0, rec["feature_acts"] > 0)
+        if "raw_grads" in rec:
+            assert rec["raw_grads"]["b_enc"] is None
+            for name in GATED_PARAMS:
+                assert_close(out["raw_grads"][name], rec["raw_grads"][name], 5e-5, f"step {s} raw grad {name}")
+                assert_close(out["grads"][name], rec["final_grads"][name], 5e-5, f"step {s} clipped+projected grad {name}")
+        if "params_after" in rec:
+            for name in GATED_PARAMS:
+                assert_close(p[name], rec["params_after"][name], 5e-5, f"step {s} param {name}")
+    assert torch.equal(since_fired, gold["since_fired"]) and torch.equal(act_freq, gold["act_freq"])
