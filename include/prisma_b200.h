@@ -292,6 +292,32 @@ PB_API int pb_mul_inplace(float* y, const float* x, int64_t n, pb_stream_t strea
 PB_API int pb_sae_ghost_rows(const float* resid, const float* rsum, float* G0, const void* scalars, float* ghost_sum, int32_t rows,
                              int32_t d, pb_stream_t stream);
 
+/* ------------------------------------------------ Gated SAE step pieces (GatedSparseAutoencoder, sae/sae.py:648-792)
+ * One encoder GEMM feeds both paths: pi = sae_in @ W_enc + b_gate, and the weight-shared magnitude pre-activation
+ * sae_in @ (W_enc * exp(r_mag)) + b_mag equals (pi - b_gate) * exp(r_mag) + b_mag.                                       */
+/* acts = [pi > 0] * relu(mag_pre) (:701-709), pi_act = relu(pi) (:769-774), optional tf32 residual planes;
+ * fired[f] += #{acts > 0}, piact_colsum[f] += sum_b pi_act, scalars.pos_count += #{acts > 0}                              */
+PB_API int pb_gated_fwd(const float* pi, const float* b_gate, const float* r_mag, const float* b_mag, float* acts, float* acts_lo,
+                        float* pi_act, float* pi_act_lo, float* fired, float* piact_colsum, void* scalars, int32_t rows, int32_t F,
+                        pb_stream_t stream);
+/* ga = 2 (via - sae_in) / rows = d aux / d via;  *aux_sum += sum (via - sae_in)^2     (_compute_aux_reconstruction_loss, :783-788) */
+PB_API int pb_gated_aux(const float* via, const float* sae_in, float* ga, float* aux_sum, int32_t rows, int32_t d, pb_stream_t stream);
+/* in: d_acts = g @ W_dec^T, d_pia = ga @ W_dec^T.  d_acts is overwritten with D = dL/d(sae_in @ W_enc)
+ * = [pi>0] (d_pia + l1_grad ||W_dec[f]||) + [pi>0][mag_pre>0] d_acts exp(r_mag); gb_gate, gb_mag, gr_mag, dsum = colsum(D) are zeroed and filled */
+PB_API int pb_gated_bwd(float* d_acts, float* D_lo, const float* d_pia, const float* pi, const float* b_gate, const float* r_mag,
+                        const float* b_mag, const float* wnorm, float l1_grad, float* gb_gate, float* gb_mag, float* gr_mag, float* dsum,
+                        int32_t rows, int32_t F, pb_stream_t stream);
+PB_API int pb_row_norms(const float* W, float* out, int32_t F, int32_t d, pb_stream_t stream);      /* out[f] = ||W[f,:]|| */
+/* gW_dec[f,:] += l1_grad * piact_colsum[f] * W_dec[f,:] / wnorm[f];  *l1_sum += piact_colsum[f] * wnorm[f]   (_compute_l1_loss, :776-781) */
+PB_API int pb_gated_l1_rows(float* gW_dec, const float* W_dec, const float* piact_colsum, const float* wnorm, float l1_grad, float* l1_sum,
+                            int32_t F, int32_t d, pb_stream_t stream);
+PB_API int pb_sumsq(const float* a, int64_t n, float* acc, pb_stream_t stream);                      /* *acc += sum a^2 */
+/* scalars.gnorm_sq (accumulated by pb_sumsq) -> grad_norm, clip_coef (train_sae.py:394-397), mse, l0 */
+PB_API int pb_sae_clip_finish(void* scalars, float max_grad_norm, int32_t rows, int32_t d, pb_stream_t stream);
+/* torch.optim.Adam on one vector parameter with the step's clip coefficient read from scalars (r_mag, b_mag) */
+PB_API int pb_adam_vec(float* p, const float* g, float* m, float* v, int32_t n, const void* scalars, float lr, float beta1, float beta2,
+                       float eps, int32_t step, pb_stream_t stream);
+
 /* ------------------------------------------------ data-parallel SAE step over NVLink peer memory
  * New functionality (the reference trains on one device): gradients are reduce-scattered by direct peer loads,
  * the owner of a feature-row slice runs clip + projection + Adam + renorm and stores the new rows into every peer

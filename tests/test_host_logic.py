@@ -173,7 +173,7 @@ def test_product_path_refuses_cpu_tensors():
 
 def test_c_abi_library_exports_every_declared_symbol():
     from vit_prisma.b200 import _lib as L
-    from vit_prisma.b200 import p2p, sae_dense, sae_engine  # noqa: F401  (register the SAE / P2P entry points)
+    from vit_prisma.b200 import p2p, sae_dense, sae_engine, sae_gated  # noqa: F401  (register the SAE / P2P entry points)
     header = open(os.path.join(ROOT, "include", "prisma_b200.h")).read()
     declared = set(re.findall(r"PB_API\s+[\w\s\*]+?\b(pb_\w+)\s*\(", header))
     assert len(declared) >= 20

@@ -370,3 +370,227 @@ extern "C" int pb_sae_ghost_rows(const float* resid, const float* rsum, float* G
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
+
+// ================================================================================================ Gated SAE (sae/sae.py:648-792)
+// The magnitude path shares the encoder matrix: sae_in @ (W_enc * exp(r_mag)) + b_mag = (pi - b_gate) * exp(r_mag) + b_mag with
+// pi = sae_in @ W_enc + b_gate, so one encoder GEMM feeds both paths and everything else below is element-wise in [tokens, d_sae].
+namespace {
+
+// forward: acts = [pi > 0] * relu(mag_pre), pi_act = relu(pi) (+ tf32 residual planes); column statistics for the step
+__global__ void __launch_bounds__(256) k_gated_fwd(const float* __restrict__ pi, const float* __restrict__ b_gate, const float* __restrict__ r_mag,
+                                                   const float* __restrict__ b_mag, float* __restrict__ acts, float* __restrict__ acts_lo,
+                                                   float* __restrict__ pi_act, float* __restrict__ pi_act_lo, float* __restrict__ fired,
+                                                   float* __restrict__ piact_colsum, SaeScalars* __restrict__ sc, int rows, int F, int rows_per_cta) {
+  __shared__ float red[8];
+  const int f = blockIdx.x * 256 + threadIdx.x;
+  float cnt = 0.f;
+  if (f < F) {
+    const float bg = b_gate[f], er = expf(r_mag[f]), bm = b_mag[f];
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    float psum = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const int64_t i = (int64_t)r * F + f;
+      const float p = pi[i];
+      const float mag = fmaf(p - bg, er, bm);
+      const float a = (p > 0.f && mag > 0.f) ? mag : 0.f;
+      const float pa = fmaxf(p, 0.f);
+      acts[i] = a;
+      pi_act[i] = pa;
+      if (acts_lo) acts_lo[i] = tf32_lo(a);
+      if (pi_act_lo) pi_act_lo[i] = tf32_lo(pa);
+      cnt += a > 0.f ? 1.f : 0.f;
+      psum += pa;
+    }
+    if (cnt > 0.f) atomicAdd(fired + f, cnt);
+    if (psum != 0.f) atomicAdd(piact_colsum + f, psum);
+  }
+  const float c = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < 8; ++i) a += red[i];
+    if (a != 0.f) atomicAdd(&sc->pos_count, a);
+  }
+}
+
+// aux reconstruction: ga = 2 (via - sae_in) / rows; *aux_sum += sum (via - sae_in)^2          (sae.py:783-788)
+__global__ void __launch_bounds__(256) k_gated_aux(const float* __restrict__ via, const float* __restrict__ sae_in, float* __restrict__ ga,
+                                                   float* __restrict__ aux_sum, int64_t n, float scale) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float e = via[i] - sae_in[i];
+    ga[i] = e * scale;
+    s = fmaf(e, e, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(aux_sum, t);
+  }
+}
+
+// backward through both encoder paths.  In: d_acts = g @ W_dec^T, d_pia = ga @ W_dec^T + (added here) l1_grad * ||W_dec[f]||.
+// Out (over d_acts): D = d_pi + d_mag * exp(r_mag) = dL/d(sae_in @ W_enc); column sums gb_gate, gb_mag, gr_mag, dsum = colsum(D).
+__global__ void __launch_bounds__(256) k_gated_bwd(float* __restrict__ d_acts, float* __restrict__ D_lo, const float* __restrict__ d_pia,
+                                                   const float* __restrict__ pi, const float* __restrict__ b_gate, const float* __restrict__ r_mag,
+                                                   const float* __restrict__ b_mag, const float* __restrict__ wnorm, float l1_grad,
+                                                   float* __restrict__ gb_gate, float* __restrict__ gb_mag, float* __restrict__ gr_mag,
+                                                   float* __restrict__ dsum, int rows, int F, int rows_per_cta) {
+  const int f = blockIdx.x * 256 + threadIdx.x;
+  if (f >= F) return;
+  const float bg = b_gate[f], er = expf(r_mag[f]), bm = b_mag[f], l1w = l1_grad * wnorm[f];
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  float sg = 0.f, sm = 0.f, sr = 0.f, sD = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const int64_t i = (int64_t)r * F + f;
+    const float p = pi[i], u = p - bg;
+    const float mag = fmaf(u, er, bm);
+    const bool on = p > 0.f;
+    const float dm = (on && mag > 0.f) ? d_acts[i] : 0.f;     // through [pi > 0] * relu(mag_pre); the Heaviside gate has no gradient
+    const float dp = on ? d_pia[i] + l1w : 0.f;               // through relu(pi): aux reconstruction + L1
+    const float D = fmaf(dm, er, dp);
+    d_acts[i] = D;
+    if (D_lo) D_lo[i] = tf32_lo(D);
+    sg += dp; sm += dm; sr = fmaf(dm * u, er, sr); sD += D;
+  }
+  atomicAdd(gb_gate + f, sg);
+  atomicAdd(gb_mag + f, sm);
+  atomicAdd(gr_mag + f, sr);
+  atomicAdd(dsum + f, sD);
+}
+
+// out[f] = ||W[f,:]||
+__global__ void __launch_bounds__(256) k_row_norms(const float* __restrict__ W, float* __restrict__ out, int F, int d) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (f >= F) return;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) { const float w = W[(int64_t)f * d + c]; s = fmaf(w, w, s); }
+  s = warp_sum(s);
+  if (lane == 0) out[f] = sqrtf(s);
+}
+
+// L1 term of the Gated SAE: l1 = coeff * mean_b sum_f pi_act[b,f] ||W_dec[f]|| (sae.py:776-781, W_dec.norm is part of the graph):
+// gW_dec[f,:] += l1_grad * colsum(pi_act)[f] * W_dec[f,:] / ||W_dec[f]|| ;  *l1_sum += colsum(pi_act)[f] * ||W_dec[f]||
+__global__ void __launch_bounds__(256) k_gated_l1_rows(float* __restrict__ gW_dec, const float* __restrict__ W_dec, const float* __restrict__ piact_colsum,
+                                                       const float* __restrict__ wnorm, float l1_grad, float* __restrict__ l1_sum, int F, int d) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (f >= F) return;
+  const float cs = piact_colsum[f], wn = wnorm[f];
+  const float coef = l1_grad * cs / wn;
+  for (int c = lane; c < d; c += 32) gW_dec[(int64_t)f * d + c] = fmaf(coef, W_dec[(int64_t)f * d + c], gW_dec[(int64_t)f * d + c]);
+  if (lane == 0 && cs != 0.f) atomicAdd(l1_sum, cs * wn);
+}
+
+struct AdamVecHyper { float lr, beta1, beta2, eps, bc1, bc2_sqrt; };
+__global__ void __launch_bounds__(256) k_adam_vec(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                  const SaeScalars* __restrict__ sc, AdamVecHyper h, int n) {
+  const float clip = sc->clip_coef;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const float gr = g[i] * clip;
+    const float mm = h.beta1 * m[i] + (1.f - h.beta1) * gr;
+    const float vv = h.beta2 * v[i] + (1.f - h.beta2) * gr * gr;
+    m[i] = mm; v[i] = vv;
+    p[i] -= (h.lr / h.bc1) * (mm / (sqrtf(vv) / h.bc2_sqrt + h.eps));
+  }
+}
+
+inline void col_grid(int rows, int F, dim3& grid, int& rpc) {
+  const int gx = (F + 255) / 256;
+  const int chunks = std::max(1, std::min(rows, (pb_sm_count() * 8 + gx - 1) / gx));
+  rpc = (rows + chunks - 1) / chunks;
+  grid = dim3(gx, (rows + rpc - 1) / rpc);
+}
+
+}  // namespace
+
+extern "C" int pb_gated_fwd(const float* pi, const float* b_gate, const float* r_mag, const float* b_mag, float* acts, float* acts_lo,
+                            float* pi_act, float* pi_act_lo, float* fired, float* piact_colsum, void* scalars, int32_t rows, int32_t F,
+                            pb_stream_t stream) {
+  PB_CHECK_ARG(pi && b_gate && r_mag && b_mag && acts && pi_act && fired && piact_colsum && scalars && rows >= 0 && F > 0,
+               "pb_gated_fwd: bad arguments");
+  if (rows == 0) return PB_OK;
+  dim3 grid; int rpc;
+  col_grid(rows, F, grid, rpc);
+  k_gated_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(pi, b_gate, r_mag, b_mag, acts, acts_lo, pi_act, pi_act_lo, fired, piact_colsum,
+                                                      (SaeScalars*)scalars, rows, F, rpc);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_gated_aux(const float* via, const float* sae_in, float* ga, float* aux_sum, int32_t rows, int32_t d, pb_stream_t stream) {
+  PB_CHECK_ARG(via && sae_in && ga && aux_sum && rows > 0 && d > 0, "pb_gated_aux: bad arguments");
+  const int64_t n = (int64_t)rows * d;
+  k_gated_aux<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(via, sae_in, ga, aux_sum, n, 2.f / (float)rows);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_gated_bwd(float* d_acts, float* D_lo, const float* d_pia, const float* pi, const float* b_gate, const float* r_mag,
+                            const float* b_mag, const float* wnorm, float l1_grad, float* gb_gate, float* gb_mag, float* gr_mag, float* dsum,
+                            int32_t rows, int32_t F, pb_stream_t stream) {
+  PB_CHECK_ARG(d_acts && d_pia && pi && b_gate && r_mag && b_mag && wnorm && gb_gate && gb_mag && gr_mag && dsum && rows >= 0 && F > 0,
+               "pb_gated_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  PB_CUDA(cudaMemsetAsync(gb_gate, 0, sizeof(float) * F, st));
+  PB_CUDA(cudaMemsetAsync(gb_mag, 0, sizeof(float) * F, st));
+  PB_CUDA(cudaMemsetAsync(gr_mag, 0, sizeof(float) * F, st));
+  PB_CUDA(cudaMemsetAsync(dsum, 0, sizeof(float) * F, st));
+  if (rows == 0) return PB_OK;
+  dim3 grid; int rpc;
+  col_grid(rows, F, grid, rpc);
+  k_gated_bwd<<<grid, 256, 0, st>>>(d_acts, D_lo, d_pia, pi, b_gate, r_mag, b_mag, wnorm, l1_grad, gb_gate, gb_mag, gr_mag, dsum, rows, F, rpc);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_row_norms(const float* W, float* out, int32_t F, int32_t d, pb_stream_t stream) {
+  PB_CHECK_ARG(W && out && F >= 0 && d > 0, "pb_row_norms: bad arguments");
+  if (F == 0) return PB_OK;
+  k_row_norms<<<(F + 7) / 8, 256, 0, (cudaStream_t)stream>>>(W, out, F, d);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_gated_l1_rows(float* gW_dec, const float* W_dec, const float* piact_colsum, const float* wnorm, float l1_grad, float* l1_sum,
+                                int32_t F, int32_t d, pb_stream_t stream) {
+  PB_CHECK_ARG(gW_dec && W_dec && piact_colsum && wnorm && l1_sum && F >= 0 && d > 0, "pb_gated_l1_rows: bad arguments");
+  if (F == 0) return PB_OK;
+  k_gated_l1_rows<<<(F + 7) / 8, 256, 0, (cudaStream_t)stream>>>(gW_dec, W_dec, piact_colsum, wnorm, l1_grad, l1_sum, F, d);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_sumsq(const float* a, int64_t n, float* acc, pb_stream_t stream) {
+  PB_CHECK_ARG(a && acc && n >= 0, "pb_sumsq: bad arguments");
+  if (n == 0) return PB_OK;
+  k_sumsq<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(a, n, acc);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_sae_clip_finish(void* scalars, float max_grad_norm, int32_t rows, int32_t d, pb_stream_t stream) {
+  PB_CHECK_ARG(scalars && rows > 0 && d > 0, "pb_sae_clip_finish: bad arguments");
+  k_grad_finish<<<1, 1, 0, (cudaStream_t)stream>>>((SaeScalars*)scalars, max_grad_norm, 1.f / ((float)rows * (float)d), 1.f / (float)rows);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_adam_vec(float* p, const float* g, float* m, float* v, int32_t n, const void* scalars, float lr, float beta1, float beta2,
+                           float eps, int32_t step, pb_stream_t stream) {
+  PB_CHECK_ARG(p && g && m && v && scalars && n >= 0 && step >= 1, "pb_adam_vec: bad arguments");
+  if (n == 0) return PB_OK;
+  AdamVecHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps;
+  h.bc1 = 1.f - powf(beta1, (float)step);
+  h.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  k_adam_vec<<<std::min((n + 255) / 256, pb_sm_count() * 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (const SaeScalars*)scalars, h, n);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}

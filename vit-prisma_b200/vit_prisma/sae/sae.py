@@ -351,19 +351,94 @@ class StandardSparseAutoencoder(SparseAutoencoder):
 
 
 class GatedSparseAutoencoder(SparseAutoencoder):
-    """Gated SAE (reference :648-792) -- listed as the next row after Standard; not built yet."""
+    """Gated SAE (reference sae/sae.py:648-792): gate path ``[sae_in @ W_enc + b_gate > 0]``, magnitude path
+    ``relu(sae_in @ (W_enc * exp(r_mag)) + b_mag)`` with the shared encoder, L1 on ``relu(pi) * ||W_dec||`` and the via-gate
+    auxiliary reconstruction loss.  Forward and training step run on ``vit_prisma/b200/sae_gated.py`` (one encoder GEMM for
+    both paths).  HookPoints fire as observers; a hook that *replaces* an activation is refused (the module-by-module route the
+    Standard SAE has is not built for this variant)."""
 
     def __init__(self, cfg):
-        raise NotImplementedError("GatedSparseAutoencoder is outside the round-1 B200 hot-path scope (SURVEY 8f, row f3)")
+        super().__init__(cfg)
+        assert self.cfg.use_ghost_grads == False, "Gated SAE does not support ghost grads"   # noqa: E712  (reference :655-657)
+        if cfg.activation_fn_str != "relu":
+            raise NotImplementedError("B200 Gated SAE: activation_fn_str must be 'relu' (the reference default)")
+        if self.dtype != torch.float32:
+            raise NotImplementedError("B200 Gated SAE runs in float32")
 
-    def encode(self, x):  # pragma: no cover
-        raise NotImplementedError
+    def initialize_sae_weights(self):                                     # reference :659-693 (plain kaiming_uniform_, no row norm)
+        enc = torch.nn.init.kaiming_uniform_(torch.empty(self.cfg.d_in, self.cfg.d_sae, dtype=self.dtype, device=self.device))
+        self.W_enc = nn.Parameter(enc.t().contiguous().t())               # [d_in, d_sae] view of feature-major storage
+        z = lambda n: nn.Parameter(torch.zeros(n, dtype=self.dtype, device=self.device))  # noqa: E731
+        self.b_gate, self.r_mag, self.b_mag = z(self.cfg.d_sae), z(self.cfg.d_sae), z(self.cfg.d_sae)
+        self.W_dec = nn.Parameter(torch.nn.init.kaiming_uniform_(torch.empty(self.cfg.d_sae, self.cfg.d_in, dtype=self.dtype, device=self.device)))
+        self.b_enc = z(self.d_sae)                                        # exists in the reference, never used by its graph
+        self.b_dec = z(self.d_in)
 
-    def decode(self, features):  # pragma: no cover
-        raise NotImplementedError
+    def _canonical_params(self):
+        if not self.W_enc.data.t().is_contiguous():
+            self.W_enc.data = self.W_enc.data.t().contiguous().t()
+        if not self.W_dec.data.is_contiguous():
+            self.W_dec.data = self.W_dec.data.contiguous()
+        return self.W_enc.data.t(), self.W_dec.data, self.b_gate.data, self.r_mag.data, self.b_mag.data, self.b_dec.data
 
-    def initialize_sae_weights(self):  # pragma: no cover
-        raise NotImplementedError
+    def step_engine(self, gemm_impl: int = L.GEMM_AUTO):
+        from vit_prisma.b200.sae_gated import SaeGatedStepEngine
+        params = self._canonical_params()
+        key = tuple(t.data_ptr() for t in params) + (gemm_impl,)
+        eng = self._engine
+        if eng is None or eng._key != key:
+            wt, wd, bg, rm, bm, bd = params
+            eng = SaeGatedStepEngine(wt, wd, bg, rm, bm, bd, l1_coefficient=self.cfg.l1_coefficient, normalize_activations=self._norm_mode,
+                                     max_grad_norm=self.cfg.max_grad_norm, gemm_impl=gemm_impl)
+            eng._key = key
+            eng._enc_version = self.W_enc._version
+            self._engine = eng
+        return eng
 
-    def forward(self, x, dead_neuron_mask=None):  # pragma: no cover
-        raise NotImplementedError
+    def _fire(self, hook: HookPoint, t: torch.Tensor) -> torch.Tensor:
+        out = hook(t)
+        if out is not t and out.data_ptr() != t.data_ptr():
+            raise NotImplementedError("B200 Gated SAE: hooks may observe activations but not replace them")
+        return t
+
+    def _run(self, x: torch.Tensor):
+        x32 = ops.cast(x, self.dtype) if x.dtype != self.dtype else x
+        lead = x32.shape[:-1]
+        x2 = x32.reshape(-1, self.d_in).contiguous()
+        eng = self.step_engine()
+        if eng._enc_version != self.W_enc._version:
+            eng.refresh_lo()
+            eng._enc_version = self.W_enc._version
+        acts = eng.forward_losses(x2, want_out=True)
+        self.ln_mu, self.ln_std = eng.mu.clone().view(*lead, 1), eng.sd.clone().view(*lead, 1)
+        sae_in = self._fire(self.hook_sae_in, eng.sae_in.clone().view(*lead, self.d_in))
+        feature_acts = self._fire(self.hook_hidden_post, acts.view(*lead, self.d_sae))
+        sae_out = self._fire(self.hook_sae_out, eng.sae_out.clone().view(*lead, self.d_in))
+        return eng, x2.shape[0], sae_in, feature_acts, sae_out
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor):
+        _, _, sae_in, feature_acts, _ = self._run(x)
+        return sae_in, feature_acts
+
+    @torch.no_grad()
+    def decode(self, features: torch.Tensor):
+        wd, bd = self.W_dec.data, self.b_dec.data
+        out, _ = ops.gemm(features, wd.t().contiguous(), bd)               # (:711-722)
+        out = self.hook_sae_out(out)
+        if self._norm_mode == "layer_norm":
+            out = ops.add(ops.mul(out, self.ln_std.expand_as(out)), self.ln_mu.expand_as(out))
+        elif self._norm_mode == "constant_norm_rescale":
+            out = ops.mul(out, self.ln_std.expand_as(out))
+        return out
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, *args, **kwargs):
+        eng, rows, _sae_in, feature_acts, sae_out = self._run(x)
+        if getattr(self.cfg, "return_out_only", False):
+            return sae_out
+        mse_loss = eng.scalars[3].clone()
+        l1_loss = eng.aux[0] * (self.l1_coefficient / rows)
+        aux_reconstruction_loss = eng.aux[1] / rows
+        loss = mse_loss + l1_loss + aux_reconstruction_loss
+        return (sae_out, feature_acts, loss, mse_loss, l1_loss, self.zero_loss.to(sae_out.device), aux_reconstruction_loss)

@@ -17,7 +17,7 @@ Notes on fidelity
     ``set_decoder_norm_to_unit_norm()`` on the reference side);
   * ``optimizer`` / ``scheduler`` returned by ``initialize_training_variables`` are light handles (``param_groups[0]["lr"]``,
     ``step()``, ``get_last_lr()``) -- the optimizer state lives in the engine's device buffers;
-  * ghost grads (``cfg.use_ghost_grads``), gated SAEs and transcoders are not built yet and raise at construction.
+  * transcoders are not built yet and raise at construction (dense ReLU + L1, ghost grads and the Gated SAE are).
 """
 from __future__ import annotations
 
@@ -176,7 +176,10 @@ class VisionSAETrainer:
 
         lr = optimizer.param_groups[0]["lr"]
         l1_loss = None
-        if cfg.activation_fn_str == "relu":                          # dense products + L1 (+ ghost grads), sae_dense.py
+        gated = cfg.architecture == "gated"
+        if gated:                                                    # one encoder GEMM for gate + magnitude paths, sae_gated.py
+            scalars = engine.train_step_gated(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores)
+        elif cfg.activation_fn_str == "relu":                        # dense products + L1 (+ ghost grads), sae_dense.py
             scalars = engine.train_step_dense(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores,
                                               use_ghost_grads=bool(cfg.use_ghost_grads), dead_feature_window=cfg.dead_feature_window)
         elif cfg.use_ghost_grads:                                    # sparse TopK gradients + ghost blocks on the dead features
@@ -186,7 +189,10 @@ class VisionSAETrainer:
         n_frac_active_tokens += sae_in.shape[0]
         mse_loss = scalars[3]
         loss = mse_loss            # TopK: loss == mse (no L1 term, train_sae.py:617-626)
-        if hasattr(engine, "aux"):                                   # device-side: loss = mse + l1 + ghost (sae.py:628)
+        if gated:                                                    # loss = mse + l1 + aux reconstruction (sae.py:744)
+            l1_loss = engine.aux[0] * (engine.l1_coefficient / sae_in.shape[0])
+            loss = loss + l1_loss + engine.aux[1] / float(sae_in.shape[0])
+        elif hasattr(engine, "aux"):                                 # device-side: loss = mse + l1 + ghost (sae.py:628)
             ghost_loss = engine.aux[1] / float(sae_in.shape[0] * engine.d)
             if cfg.activation_fn_str != "topk":
                 l1_loss = engine.aux[0] * (engine.l1_coefficient / sae_in.shape[0])
