@@ -97,6 +97,41 @@ def test_gated_step_midsize_matches_oracle(impl):
     assert abs(t["grad_norm"] - out["grad_norm"].item()) <= 1e-3 * out["grad_norm"].item()
 
 
+@pytest.mark.parametrize("variant", ["relu", "relu_ghost", "topk_ghost", "gated"])
+def test_trainer_steps_every_variant_on_synthetic_activations(variant):
+    """VisionSAETrainer.train_step (train_sae.py:278-411) dispatches to the dense / ghost / gated engines and the loss goes down."""
+    from vit_prisma.sae.config import VisionModelSAERunnerConfig
+    from vit_prisma.sae.train_sae import VisionSAETrainer
+    from vit_prisma.sae.training.activations_store import SyntheticActivationsStore
+    kw = dict(d_in=64, expansion_factor=8, _device="cuda", n_checkpoints=0, log_to_wandb=False, b_dec_init_method="mean", train_batch_size=256,
+              lr_warm_up_steps=5, checkpoint_path="/tmp/prisma_b200_ckpt", lr=2e-3, l1_coefficient=1e-3, num_epochs=1)
+    if variant.startswith("relu"):
+        kw.update(activation_fn_str="relu", activation_fn_kwargs={})
+    elif variant == "topk_ghost":
+        kw.update(activation_fn_str="topk", activation_fn_kwargs={"k": 8})
+    else:
+        kw.update(activation_fn_str="relu", activation_fn_kwargs={}, architecture="gated")
+    if variant.endswith("ghost"):
+        kw.update(use_ghost_grads=True, dead_feature_window=2)
+    cfg = VisionModelSAERunnerConfig(**kw)
+    torch.manual_seed(0)
+    store = SyntheticActivationsStore(cfg, pool_tokens=1 << 14, seed=1)
+    trainer = VisionSAETrainer(cfg, model=None, dataset=None, activations_store=store)
+    act_freq, since_fired, n_frac, opt, sched = trainer.initialize_training_variables()
+    trainer.initialize_geometric_medians()
+    losses = []
+    for step in range(40):
+        loss, mse, l1, l0, act_freq, since_fired, n_frac = trainer.train_step(
+            trainer.sparse_coder, opt, sched, act_freq, since_fired, n_frac, store.next_batch(), step, step * cfg.train_batch_size)
+        losses.append(float(loss))
+    assert all(math.isfinite(v) for v in losses)
+    assert losses[-1] < 0.9 * losses[0], (variant, losses[0], losses[-1])
+    assert (l1 is None) == (variant == "topk_ghost")
+    norms = trainer.sparse_coder.W_dec.data.norm(dim=1)
+    assert torch.allclose(norms, torch.ones_like(norms), atol=1e-5)
+    assert n_frac == 40 * 256 and float(act_freq.sum()) > 0
+
+
 def test_gated_module_forward_tuple_and_trainer_dispatch():
     """GatedSparseAutoencoder.forward returns the reference's 7-tuple (sae.py:753-761); step_engine() is the gated engine."""
     from vit_prisma.b200.sae_gated import SaeGatedStepEngine

@@ -79,8 +79,6 @@ class VisionSAETrainer:
             self.sparse_coder = StandardSparseAutoencoder(cfg)
         else:
             raise ValueError(f"Loading of {cfg.architecture} not supported")
-        if cfg.use_ghost_grads:
-            raise NotImplementedError("ghost-grad auxiliary loss is not built on the B200 path yet (SURVEY 8a b8)")
         self.dataset, self.eval_dataset = dataset, eval_dataset
         self.activations_store = activations_store if activations_store is not None else self.initialize_activations_store(dataset, eval_dataset)
         if not cfg.wandb_project:
