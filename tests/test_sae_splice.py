@@ -1,0 +1,69 @@
+"""HookedSAEViT (reference models/base_vit.py:827-1086): SAE splice bookkeeping on CPU, splice numerics on the GPU."""
+import pytest
+import torch
+
+from vit_prisma.configs.HookedViTConfig import HookedViTConfig
+from vit_prisma.models.base_vit import HookedSAEViT
+from vit_prisma.prisma_tools.hook_point import HookPoint
+from vit_prisma.sae.config import VisionModelSAERunnerConfig
+from vit_prisma.sae.sae import StandardSparseAutoencoder
+
+VIT = dict(n_layers=2, d_model=64, d_head=16, n_heads=4, d_mlp=128, patch_size=16, image_size=32, n_classes=10)
+
+
+def _sae(device, layer=0, k=8):
+    cfg = VisionModelSAERunnerConfig(d_in=64, expansion_factor=4, activation_fn_str="topk", activation_fn_kwargs={"k": k}, _device=device,
+                                     _dtype="float32", hook_point_layer=layer, layer_subtype="hook_resid_post", log_to_wandb=False,
+                                     n_checkpoints=0, checkpoint_path="/tmp/unused")
+    torch.manual_seed(layer)
+    return StandardSparseAutoencoder(cfg)
+
+
+def test_splice_bookkeeping_on_cpu():
+    model = HookedSAEViT(HookedViTConfig(**VIT))
+    names_before = list(model.hook_dict)
+    sae = _sae("cpu")
+    assert sae.cfg.hook_point == "blocks.0.hook_resid_post"
+    model.add_sae(sae)
+    assert model.blocks[0].hook_resid_post is sae and model.acts_to_saes == {"blocks.0.hook_resid_post": sae}
+    assert sae.cfg.return_out_only is True
+    for inner in ("hook_sae_in", "hook_hidden_pre", "hook_hidden_post", "hook_sae_out"):
+        assert f"blocks.0.hook_resid_post.{inner}" in model.hook_dict
+    assert "blocks.0.hook_resid_post" not in model.hook_dict
+    assert "SAE spliced in" in model._fused_blocker(torch.zeros(1))
+    other = _sae("cpu")
+    with model.saes(saes=[other], use_error_term=True):
+        assert model.blocks[0].hook_resid_post is other and other.use_error_term is True
+    assert model.blocks[0].hook_resid_post is sae and not hasattr(other, "_original_use_error_term") and other.use_error_term is False
+    model.reset_saes()
+    assert model.acts_to_saes == {} and isinstance(model.blocks[0].hook_resid_post, HookPoint)
+    assert list(model.hook_dict) == names_before and model.hook_dict["blocks.0.hook_resid_post"].name == "blocks.0.hook_resid_post"
+    with pytest.raises(ValueError):
+        model.reset_saes(["a", "b"], [None])
+
+
+@pytest.mark.gpu
+def test_spliced_forward_equals_replacing_the_activation_by_hand():
+    model = HookedSAEViT(HookedViTConfig(**VIT)).to("cuda").eval()
+    sae = _sae("cuda", layer=1)
+    sae.set_decoder_norm_to_unit_norm()
+    x = torch.randn(3, 3, 32, 32, device="cuda")
+    clean = model(x)
+    assert model.last_route == "fused"
+    spliced, cache = model.run_with_cache_with_saes(x, saes=[sae])
+    assert model.last_route.startswith("hooked: SAE spliced in")
+    name = "blocks.1.hook_resid_post"
+    for inner in ("hook_sae_in", "hook_hidden_pre", "hook_hidden_post", "hook_sae_out"):
+        assert f"{name}.{inner}" in cache
+    assert name not in cache and cache[f"{name}.hook_hidden_post"].shape == (3, 5, 256)
+    assert int((cache[f"{name}.hook_hidden_post"] > 0).sum(-1).max()) <= 8
+    # the same computation spelled out with a replacing hook on the un-spliced model
+    assert model.acts_to_saes == {} and isinstance(model.blocks[1].hook_resid_post, HookPoint)
+    sae.cfg.return_out_only = True
+    by_hand = model.run_with_hooks(x, fwd_hooks=[(name, lambda act, hook: sae(act))])
+    assert torch.allclose(spliced, by_hand, rtol=1e-5, atol=1e-6)
+    assert not torch.allclose(spliced, clean, rtol=1e-3, atol=1e-4), "an untrained SAE must change the output"
+    # error term: the clean activation flows on, so the output equals the clean run while the SAE's hook points still fire
+    out_err, cache_err = model.run_with_cache_with_saes(x, saes=[sae], use_error_term=True)
+    assert torch.allclose(out_err, clean, rtol=1e-5, atol=1e-6) and f"{name}.hook_sae_out" in cache_err
+    assert model(x) is not None and model.last_route == "fused"

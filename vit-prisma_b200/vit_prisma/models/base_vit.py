@@ -18,7 +18,8 @@ from __future__ import annotations
 
 import logging
 import os
-from typing import Dict, Optional, Tuple, Union
+from contextlib import contextmanager
+from typing import Dict, List, Optional, Tuple, Union
 
 import torch
 import torch.nn as nn
@@ -300,3 +301,109 @@ class HookedViT(HookedRootModule):
     b_out = property(lambda self: self._stack(lambda b: b.mlp.b_out))
     W_H = property(lambda self: self.head.W_H)
     b_H = property(lambda self: self.head.b_H)
+
+
+# ------------------------------------------------------------------------------------------------ SAE splice
+def _walk_to_parent(root, dotted: str):
+    """('blocks.3.hook_resid_post') -> (module blocks[3], 'hook_resid_post'); numeric parts index containers."""
+    parts = dotted.split(".")
+    obj = root
+    for part in parts[:-1]:
+        obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+    return obj, parts[-1]
+
+
+class HookedSAEViT(HookedViT):
+    """HookedViT with sparse autoencoders spliced in at hook points (reference models/base_vit.py:827-1086).
+
+    ``add_sae`` puts the SAE module in the place of the HookPoint named ``sae.cfg.hook_point``: the block calls it where it
+    called the hook, the SAE (``cfg.return_out_only = True``) hands back its reconstruction, and its own hook points appear in
+    ``hook_dict`` / caches as ``<hook_point>.hook_sae_in`` ... ``.hook_sae_out``.  While any SAE is attached the model runs its
+    module-by-module route (every op still a C-ABI kernel; the SAE forward is the fused encode -> TopK -> decode engine).
+    The reference reads ``sae.cfg.hook_name`` in ``saes()`` but ``sae.cfg.hook_point`` in ``add_sae`` (:857 vs :1078); the config
+    only defines ``hook_point``, which is what both use here."""
+
+    def __init__(self, *model_args, **model_kwargs):
+        super().__init__(*model_args, **model_kwargs)
+        self.acts_to_saes: Dict[str, torch.nn.Module] = {}
+
+    def _fused_blocker(self, x):
+        if self.acts_to_saes:
+            return f"SAE spliced in at {', '.join(self.acts_to_saes)}"
+        return super()._fused_blocker(x)
+
+    def add_sae(self, sae, use_error_term: Optional[bool] = None):
+        act_name = sae.cfg.hook_point
+        if act_name not in self.acts_to_saes and act_name not in self.hook_dict:
+            logging.warning(f"No hook found for {act_name}. Skipping. Check model.hook_dict for available hooks.")
+            return
+        if use_error_term is not None:
+            if not hasattr(sae, "_original_use_error_term"):
+                sae._original_use_error_term = getattr(sae, "use_error_term", False)
+            sae.use_error_term = use_error_term
+        sae.cfg.return_out_only = True
+        self.acts_to_saes[act_name] = sae
+        parent, leaf = _walk_to_parent(self, act_name)
+        setattr(parent, leaf, sae)
+        self.setup()
+
+    def _reset_sae(self, act_name: str, prev_sae=None):
+        if act_name not in self.acts_to_saes:
+            logging.warning(f"No SAE is attached to {act_name}. There's nothing to reset.")
+            return
+        current = self.acts_to_saes[act_name]
+        if hasattr(current, "_original_use_error_term"):
+            current.use_error_term = current._original_use_error_term
+            delattr(current, "_original_use_error_term")
+        parent, leaf = _walk_to_parent(self, act_name)
+        if prev_sae:
+            setattr(parent, leaf, prev_sae)
+            self.acts_to_saes[act_name] = prev_sae
+        else:
+            setattr(parent, leaf, HookPoint())
+            del self.acts_to_saes[act_name]
+
+    def reset_saes(self, act_names: Optional[Union[str, List[str]]] = None, prev_saes: Optional[list] = None):
+        if isinstance(act_names, str):
+            act_names = [act_names]
+        elif act_names is None:
+            act_names = list(self.acts_to_saes.keys())
+        if prev_saes:
+            if len(act_names) != len(prev_saes):
+                raise ValueError("act_names and prev_saes must have the same length")
+        else:
+            prev_saes = [None] * len(act_names)
+        for act_name, prev in zip(act_names, prev_saes):
+            self._reset_sae(act_name, prev)
+        self.setup()
+
+    @contextmanager
+    def saes(self, saes=(), reset_saes_end: bool = True, use_error_term: Optional[bool] = None):
+        """Temporarily attach ``saes``; previously attached SAEs at the same hook points come back on exit."""
+        if isinstance(saes, torch.nn.Module):
+            saes = [saes]
+        names, previous = [], []
+        try:
+            for sae in saes:
+                names.append(sae.cfg.hook_point)
+                previous.append(self.acts_to_saes.get(sae.cfg.hook_point))
+                self.add_sae(sae, use_error_term=use_error_term)
+            yield self
+        finally:
+            if reset_saes_end:
+                self.reset_saes(names, previous)
+
+    def run_with_saes(self, *model_args, saes=(), reset_saes_end: bool = True, use_error_term: Optional[bool] = None, **model_kwargs):
+        with self.saes(saes=saes, reset_saes_end=reset_saes_end, use_error_term=use_error_term):
+            return self(*model_args, **model_kwargs)
+
+    def run_with_cache_with_saes(self, *model_args, saes=(), reset_saes_end: bool = True, use_error_term: Optional[bool] = None,
+                                 return_cache_object: bool = True, remove_batch_dim: bool = False, **kwargs):
+        with self.saes(saes=saes, reset_saes_end=reset_saes_end, use_error_term=use_error_term):
+            return self.run_with_cache(*model_args, return_cache_object=return_cache_object, remove_batch_dim=remove_batch_dim, **kwargs)
+
+    def run_with_hooks_with_saes(self, *model_args, saes=(), reset_saes_end: bool = True, fwd_hooks=(), bwd_hooks=(),
+                                 reset_hooks_end: bool = True, clear_contexts: bool = False, **model_kwargs):
+        with self.saes(saes=saes, reset_saes_end=reset_saes_end):
+            return self.run_with_hooks(*model_args, fwd_hooks=list(fwd_hooks), bwd_hooks=list(bwd_hooks), reset_hooks_end=reset_hooks_end,
+                                       clear_contexts=clear_contexts, **model_kwargs)

@@ -323,15 +323,17 @@ class StandardSparseAutoencoder(SparseAutoencoder):
             sae_out2, _idx, _val = eng.forward(x2)
             sae_out = sae_out2.clone().view(*lead, self.d_in)
             mse_loss = eng.scalars[3].clone()
-            if getattr(self.cfg, "return_out_only", False):
-                return sae_out
+            if getattr(self.cfg, "return_out_only", False):      # spliced into HookedSAEViT (reference :636-640)
+                # use_error_term: sae_out + (x - sae_out).detach() == x -- the clean activation flows on, the SAE's hooks still fired
+                return x if getattr(self, "use_error_term", False) else sae_out
             feature_acts = eng.dense_feature_acts().view(*lead, self.d_sae)
             hidden_pre2 = eng.hidden_pre
         else:
             _, feature_acts, _hidden_pre = self.encode(x32, return_hidden_pre=True)
             sae_out = self.decode(feature_acts)
-            if getattr(self.cfg, "return_out_only", False):
-                return sae_out
+            if getattr(self.cfg, "return_out_only", False):      # spliced into HookedSAEViT (reference :636-640)
+                # use_error_term: sae_out + (x - sae_out).detach() == x -- the clean activation flows on, the SAE's hooks still fired
+                return x if getattr(self, "use_error_term", False) else sae_out
             mse_loss = sae_mse(x2, sae_out.reshape(-1, self.d_in).contiguous())
             hidden_pre2 = _hidden_pre.reshape(-1, self.d_sae)
         ghost_loss = self.zero_loss.to(sae_out.device)
