@@ -15,7 +15,11 @@
 // ([16][T] elements of T, already rounded), so the copy-out is a linear vector memcpy of one contiguous run.
 // Rounding points follow the reference graph: scores = round(round(q.k) / scale); pattern = round(softmax);
 // z = round(pattern @ v) with the rounded pattern as the operand.
+#include <stdlib.h>
+
 #include "common.cuh"
+
+int pb_attention_long(const PbAttention* p, cudaStream_t st);   // attention_long.cu
 
 namespace {
 
@@ -350,6 +354,11 @@ template <typename T>
 int dispatch_mma(const PbAttention* p, cudaStream_t st) {
   if (p->T <= 64) return launch_mma<T, 8, 4>(p, st);
   if (p->T <= 128) return launch_mma<T, 16, 4>(p, st);
+  // longer rows: K / V streamed in 64-key chunks, two passes (attention_long.cu); PB_ATTN_LONG=0 keeps the whole-row kernels
+  // below for cross-checks (T <= 272)
+  static int use_long = -1;
+  if (use_long < 0) { const char* e = getenv("PB_ATTN_LONG"); use_long = (e && !strcmp(e, "0")) ? 0 : 1; }
+  if (use_long) return pb_attention_long(p, st);
   if (p->T <= 208) return launch_mma<T, 26, 2>(p, st);
   if (p->T <= 272) return launch_mma<T, 34, 2>(p, st);
   return PB_EUNSUPPORTED;
