@@ -146,32 +146,60 @@ def cpu_vit_images_per_sec(budget_s=12.0, batch=16, threads=None, cfg=None, laye
 
 
 def run_reference_arm(args):
+    """The reference's own CPU path (its restatement, oracle/: /root/reference does not exist on the GPU box) on this box's host
+    cores, same metric / unit / workload as the product arm, each step a bounded sample of that workload.  Rank 0 only."""
     world, rank, _ = _dist()
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    from oracle.vit_oracle import CLIP_B32, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
     threads = _cpu_cores()
     torch.set_num_threads(threads)
-    cfg = dict(CLIP_B32)
-    sd = recipe_state_dict(state_dict_shapes(cfg), 1234)
-    batch = 16  # bounded sample of the batch-512 workload: per-image cost is flat in batch on CPU
-    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(0))
-    with torch.no_grad():
-        for _ in range(max(1, min(warm, 2))):
-            vit_forward_with_cache(sd, cfg, x)
+    if args.workload == "sae":
+        from oracle.sae_oracle import new_adam_state, sae_train_step
+        d, F, k = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"], SAE_CFG["k"]
+        p0 = sae_init_params(d, F)
+        p = {"W_enc": p0["W_encT"].t().contiguous(), "W_dec": p0["W_dec"], "b_enc": p0["b_enc"], "b_dec": p0["b_dec"]}
+        state = new_adam_state(p)
+        batch = 1024   # bounded sample of the 4096-token step: the dense products are linear in the token count
+        x = sae_pool(batch, d)
+        for i in range(max(1, min(warm, 2))):
+            sae_train_step(p, state, x, k, 1e-3, i + 1)
         t0 = time.perf_counter()
-        for _ in range(steps):
-            vit_forward_with_cache(sd, cfg, x)
+        for i in range(steps):
+            sae_train_step(p, state, x, k, 1e-3, i + 3)
         dt = time.perf_counter() - t0
-    v = steps * batch / dt
-    line = {"impl": "reference", "metric": "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)", "value": v,
-            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "vit_b32_run_with_cache_all_hooks", "batch_per_step": batch, "note": "bounded sample of the batch-512 workload on host cores"},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} steps x batch {batch}, oracle/vit_oracle.py (CPU restatement of the reference path)"},
-            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        v, unit = steps * batch / dt, "tokens/s"
+        metric = "SAE training tokens/sec (TopK SAE, d_model=768, dict=768x32, k=32)"
+        config = {"workload": "sae_topk_768x24576_k32", "tokens_per_step": batch, "note": "bounded sample of the 4096-token step on host cores"}
+        sample = f"{steps} train steps x {batch} tokens, oracle/sae_oracle.py (CPU restatement of the reference train_step)"
+    else:
+        from oracle.vit_oracle import CLIP_B32, CLIP_L14, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
+        l14 = args.model == "l14"
+        cfg = dict(CLIP_L14 if l14 else CLIP_B32)
+        kw = {}
+        if l14:
+            name = f"blocks.{args.layer}.hook_resid_post"
+            kw = dict(names_filter=lambda n: n == name, stop_at_layer=args.layer + 1)
+        sd = recipe_state_dict(state_dict_shapes(cfg), 1234)
+        batch = 4 if l14 else 16  # bounded sample of the batch-512 workload: per-image cost is flat in batch on CPU
+        x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+        with torch.no_grad():
+            for _ in range(max(1, min(warm, 2))):
+                vit_forward_with_cache(sd, cfg, x, **kw)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                vit_forward_with_cache(sd, cfg, x, **kw)
+            dt = time.perf_counter() - t0
+        v, unit = steps * batch / dt, "images/s"
+        metric = (f"run_with_cache images/sec (CLIP ViT-L/14, blocks.{args.layer}.hook_resid_post, stop_at_layer={args.layer + 1})" if l14
+                  else "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)")
+        config = {"workload": f"vit_l14_run_with_cache_resid_post_l{args.layer}" if l14 else "vit_b32_run_with_cache_all_hooks",
+                  "batch_per_step": batch, "note": "bounded sample of the product arm's batch on host cores"}
+        sample = f"{steps} steps x batch {batch}, oracle/vit_oracle.py (CPU restatement of the reference path)"
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": config, "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
