@@ -145,6 +145,10 @@ class VisionSAETrainer:
         then the parameters move into NVLink peer-visible buffers (sae.enable_data_parallel)."""
         if self.p2p_group is None or self.p2p_group.world == 1:
             return
+        cfg = self.cfg
+        if cfg.architecture == "gated" or cfg.activation_fn_str != "topk" or cfg.use_ghost_grads:
+            raise NotImplementedError("data-parallel SAE training over NVLink peer memory covers the TopK step (standard architecture, "
+                                      "no ghost grads); the dense / ghost / gated steps run single-GPU")
         import torch.distributed as dist
         for prm in self._canonical_param_storages():
             dist.broadcast(prm, src=0)
