@@ -128,6 +128,24 @@ class VisionActivationsStore:
             return torch.zeros((0, num_layers, d_in), dtype=self.cfg.dtype, device=self.cfg.device)
         return torch.cat(parts, dim=0)
 
+    def generate_cached_activations_from_dataset(self, tokens_per_file: int = 1_000_000, shuffle_data: bool = False) -> int:
+        """Write the dataset's activations as the reference's disk cache (reference :505-574): fp16 ``{idx}.pt`` files of
+        ``[tokens, n_layers, d_in]``, ``tokens_per_file`` tokens each (the last one holds the remainder), readable by
+        ``_load_cached_activations`` / ``CacheVisionActivationStore`` here and in the reference.  Returns the number of files."""
+        cfg = self.cfg
+        os.makedirs(cfg.cached_activations_path, exist_ok=True)
+        loader = DataLoader(self.dataset, batch_size=cfg.store_batch_size, shuffle=shuffle_data, num_workers=getattr(cfg, "num_workers", 0),
+                            drop_last=False)
+        n_layers = len(self._layers())
+        shard = _ShardWriter(cfg.cached_activations_path, tokens_per_file)
+        for batch in loader:
+            images = batch[0] if isinstance(batch, (tuple, list)) else batch
+            acts = self.get_activations(images.to(cfg.device))              # [b, T, n_layers, d_in]
+            if getattr(cfg, "use_patches_only", False):
+                acts = acts[:, 1:, :, :]
+            shard.add(acts.reshape(-1, n_layers, cfg.d_in).to(torch.float16))
+        return shard.close()
+
     def get_data_loader(self) -> Iterator[Any]:
         half = self.cfg.n_batches_in_buffer // 2
         mixing = torch.cat([self.get_buffer(half), self.storage_buffer], dim=0)
@@ -142,6 +160,34 @@ class VisionActivationsStore:
         except StopIteration:
             self.dataloader = self.get_data_loader()
             return next(self.dataloader)
+
+
+class _ShardWriter:
+    """Cuts a stream of ``[tokens, n_layers, d_in]`` blocks into ``{idx}.pt`` files of exactly ``tokens_per_file`` tokens."""
+
+    def __init__(self, directory: str, tokens_per_file: int):
+        self.dir, self.per_file = directory, int(tokens_per_file)
+        self.pending: list = []
+        self.n_pending = 0
+        self.n_files = 0
+
+    def _flush(self, n: int) -> None:
+        block = torch.cat(self.pending, dim=0)
+        torch.save(block[:n].cpu().contiguous(), os.path.join(self.dir, f"{self.n_files}.pt"))
+        self.n_files += 1
+        rest = block[n:]
+        self.pending, self.n_pending = ([rest], rest.shape[0]) if rest.shape[0] else ([], 0)
+
+    def add(self, block: torch.Tensor) -> None:
+        self.pending.append(block)
+        self.n_pending += block.shape[0]
+        while self.n_pending >= self.per_file:
+            self._flush(self.per_file)
+
+    def close(self) -> int:
+        if self.n_pending:
+            self._flush(self.n_pending)
+        return self.n_files
 
 
 class SyntheticActivationsStore:
