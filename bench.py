@@ -1,25 +1,37 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json's metric on a B200: HookedViT.run_with_cache images/sec (+ SAE tokens/sec).
+"""bench.py -- BASELINE.json's metric on B200s: SAE training tokens/sec + run_with_cache images/sec, % of roofline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload vit|sae]
-                    [--dtype fp32|bf16] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|sae|vit]
+                    [--dtype fp32|bf16] [--batch B] [--model b32|l14]
 
-Prints ONE JSON line (contract in the task statement):
-  value      whole-job throughput with inputs resident in HBM (device-timed, CUDA events, max over ranks)
-  e2e        same metric through the public API with HOST (pinned) inputs: H2D of the batch + the call + D2H
-             of the model output inside the timed region
-  roofline   dominant kernel (MLP-in GEMM with its dual hook-point epilogue), algorithmic flops / CUDA-event time
-             against MEASURED_PEAKS.json
-  cpu_baseline  the oracle port (oracle/vit_oracle.py) timed on this box's host cores on a bounded sample
---impl reference times the CPU implementation (oracle port; /root/reference does not exist on the GPU box).
-A "step" = one run_with_cache over one synthetic batch (cfg #2: CLIP ViT-B/32 geometry, batch 512, all 214 hook points).
+The default invocation (what the driver runs) measures BOTH hot paths and prints ONE JSON line:
+
+  top level    the SAE training step (cfg #3: d_model 768, dict 768 x 32, TopK k = 32, 4096 tokens per step per GPU, fp32) driven
+               through the public ``VisionSAETrainer.train_step`` -- the first half of BASELINE.json's metric and the only path with
+               a collective (N > 1: NVLink peer-memory reduce-scatter + sharded Adam + all-gather, no NCCL on the data path);
+  "secondary"  the complete record of ``HookedViT.run_with_cache`` (cfg #2: CLIP ViT-B/32, batch 512 per GPU, all hook points).
+
+Per record:
+  value      whole-job throughput with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e        the same metric through the public API with HOST (pinned) inputs: H2D of the step's input + the call + D2H of the
+             step's result inside the timed region
+  roofline   SAE: the step's algorithmic bytes (80 d F + 8 Bt d) / step time against the measured HBM copy
+             bandwidth, plus live CUDA-event timings of every stage; ViT: the dominant GEMM's algorithmic flops against the
+             measured bf16 peak.  ``traffic`` is read from the committed ncu summary under profiles/ (null if none matches).
+  cpu_baseline  the oracle port (oracle/*.py) timed on this box's host cores on a bounded sample
+  dp_parity  (N > 1) after the timed region every rank re-trains the reference-made fixture tests/golden/sae_tiny_b.pt through
+             ``VisionSAETrainer(p2p_group=...)`` and compares losses, TopK indices, parameters and counters with the
+             single-process reference run; a mismatch makes the process exit non-zero.
+``--impl reference`` times the CPU implementation (the oracle port; /root/reference does not exist on the GPU box).
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
-import subprocess
+import re
 import sys
 import threading
 import time
@@ -30,6 +42,9 @@ sys.path.insert(0, os.path.join(ROOT, "vit-prisma_b200"))
 
 import torch  # noqa: E402
 
+SAE_CFG = dict(d_in=768, expansion=32, k=32, batch=4096)     # BASELINE.json configs[2]
+POOL_BATCHES = 16                                            # synthetic activation pool = 16 steps' worth of tokens (201 MB > L2)
+
 
 def _peaks():
     try:
@@ -39,6 +54,33 @@ def _peaks():
                 "source": "measured"}
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic(kernel_regex: str, prefer: str = ""):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the first kernel matching ``kernel_regex`` in the newest
+    committed ``profiles/*_ncu_summary.txt`` (tools/ncu_summary.py output; file names sort by round).  Returns (bytes, file) or
+    (None, None): the roofline's ``traffic`` is never a literal typed into this file."""
+    prof = os.path.join(ROOT, "profiles")
+    try:
+        files = sorted((f for f in os.listdir(prof) if f.endswith("_ncu_summary.txt")), reverse=True)
+    except OSError:
+        return None, None
+    files.sort(key=lambda f: (prefer not in f) if prefer else False)
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for fn in files:
+        cur, got = None, {}
+        for line in open(os.path.join(prof, fn)):
+            if line.startswith("== "):
+                if cur and len(got) == 2:
+                    return got["r"] + got["w"], "profiles/" + fn
+                cur, got = (line if re.search(kernel_regex, line) else None), {}
+            elif cur:
+                m = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+                if m and m.group(3) in unit:
+                    got[m.group(1)[0]] = float(m.group(2)) * unit[m.group(3)]
+        if cur and len(got) == 2:
+            return got["r"] + got["w"], "profiles/" + fn
+    return None, None
 
 
 class ClockSampler:
@@ -96,10 +138,7 @@ class ClockSampler:
 
 
 def _dist():
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return world, rank, local
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 def _cpu_cores():
@@ -118,7 +157,36 @@ def _cpu_cores():
     return n
 
 
-# ------------------------------------------------------------------ CPU (oracle port) arm
+class Ctx:
+    """Rank bookkeeping + the barrier / max-over-ranks helpers of the timing contract."""
+
+    def __init__(self):
+        self.world, self.rank, self.local = _dist()
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)      # rendezvous, IPC-handle exchange, timing reductions
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+# =====================================================================================================================
+# CPU legs (the only code in this file that touches oracle/)
+# =====================================================================================================================
 def cpu_vit_images_per_sec(budget_s=12.0, batch=16, threads=None, cfg=None, layer=None):
     """Oracle port on the host cores; ``layer`` = the activation-store call (names_filter one resid_post + stop_at_layer)."""
     from oracle.vit_oracle import CLIP_B32, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
@@ -145,23 +213,48 @@ def cpu_vit_images_per_sec(budget_s=12.0, batch=16, threads=None, cfg=None, laye
             "sample": f"{n} x run_with_cache(batch {batch}) d_model {cfg['d_model']} x {cfg['n_layers']} layers fp32, {what}, oracle/vit_oracle.py, {dt:.1f}s"}
 
 
+def _cpu_sae_setup(batch):
+    from oracle.sae_oracle import new_adam_state
+    from vit_prisma.b200.synthetic import activation_pool, sae_init_params
+    d, F = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"]
+    p0 = sae_init_params(d, F)
+    p = {"W_enc": p0["W_encT"].t().contiguous(), "W_dec": p0["W_dec"], "b_enc": p0["b_enc"], "b_dec": p0["b_dec"]}
+    return p, new_adam_state(p), activation_pool(batch, d)
+
+
+def cpu_sae_tokens_per_sec(budget_s=12.0, threads=None, batch=1024):
+    """Oracle port of the reference train_step (dense autograd-equivalent formulas) on host cores, bounded sample."""
+    from oracle.sae_oracle import sae_train_step
+    threads = threads or _cpu_cores()
+    torch.set_num_threads(threads)
+    p, state, x = _cpu_sae_setup(batch)
+    k = SAE_CFG["k"]
+    sae_train_step(p, state, x, k, 1e-3, 1)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        sae_train_step(p, state, x, k, 1e-3, n + 2)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or n >= 16:
+            break
+    return {"value": n * batch / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": f"{n} train steps x {batch} tokens (of the 4096-token step), d=768 F=24576 k=32 fp32, oracle/sae_oracle.py, {dt:.1f}s"}
+
+
 def run_reference_arm(args):
     """The reference's own CPU path (its restatement, oracle/: /root/reference does not exist on the GPU box) on this box's host
-    cores, same metric / unit / workload as the product arm, each step a bounded sample of that workload.  Rank 0 only."""
+    cores, same metric / unit / workload as the product arm's headline, each step a bounded sample of that workload.  Rank 0 only."""
     world, rank, _ = _dist()
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
     threads = _cpu_cores()
     torch.set_num_threads(threads)
-    if args.workload == "sae":
-        from oracle.sae_oracle import new_adam_state, sae_train_step
-        d, F, k = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"], SAE_CFG["k"]
-        p0 = sae_init_params(d, F)
-        p = {"W_enc": p0["W_encT"].t().contiguous(), "W_dec": p0["W_dec"], "b_enc": p0["b_enc"], "b_dec": p0["b_dec"]}
-        state = new_adam_state(p)
+    if args.workload in ("all", "sae"):
+        from oracle.sae_oracle import sae_train_step
         batch = 1024   # bounded sample of the 4096-token step: the dense products are linear in the token count
-        x = sae_pool(batch, d)
+        p, state, x = _cpu_sae_setup(batch)
+        k = SAE_CFG["k"]
         for i in range(max(1, min(warm, 2))):
             sae_train_step(p, state, x, k, 1e-3, i + 1)
         t0 = time.perf_counter()
@@ -169,8 +262,9 @@ def run_reference_arm(args):
             sae_train_step(p, state, x, k, 1e-3, i + 3)
         dt = time.perf_counter() - t0
         v, unit = steps * batch / dt, "tokens/s"
-        metric = "SAE training tokens/sec (TopK SAE, d_model=768, dict=768x32, k=32)"
-        config = {"workload": "sae_topk_768x24576_k32", "tokens_per_step": batch, "note": "bounded sample of the 4096-token step on host cores"}
+        metric = SAE_METRIC
+        config = {"workload": "sae_topk_train_step", "d_in": SAE_CFG["d_in"], "d_sae": SAE_CFG["d_in"] * SAE_CFG["expansion"], "k": k,
+                  "tokens_per_step": batch, "note": "bounded sample of the 4096-token step on host cores"}
         sample = f"{steps} train steps x {batch} tokens, oracle/sae_oracle.py (CPU restatement of the reference train_step)"
     else:
         from oracle.vit_oracle import CLIP_B32, CLIP_L14, recipe_state_dict, state_dict_shapes, vit_forward_with_cache
@@ -191,8 +285,7 @@ def run_reference_arm(args):
                 vit_forward_with_cache(sd, cfg, x, **kw)
             dt = time.perf_counter() - t0
         v, unit = steps * batch / dt, "images/s"
-        metric = (f"run_with_cache images/sec (CLIP ViT-L/14, blocks.{args.layer}.hook_resid_post, stop_at_layer={args.layer + 1})" if l14
-                  else "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)")
+        metric = vit_metric(l14, args.layer)
         config = {"workload": f"vit_l14_run_with_cache_resid_post_l{args.layer}" if l14 else "vit_b32_run_with_cache_all_hooks",
                   "batch_per_step": batch, "note": "bounded sample of the product arm's batch on host cores"}
         sample = f"{steps} steps x batch {batch}, oracle/vit_oracle.py (CPU restatement of the reference path)"
@@ -203,14 +296,20 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------ GPU arm
-def build_model(dtype, device, cfg=None):
-    from oracle.vit_oracle import CLIP_B32, recipe_state_dict
+# =====================================================================================================================
+# Path A: HookedViT.run_with_cache
+# =====================================================================================================================
+def vit_metric(l14, layer):
+    return (f"run_with_cache images/sec (CLIP ViT-L/14, blocks.{layer}.hook_resid_post, stop_at_layer={layer + 1})" if l14
+            else "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)")
+
+
+def build_model(dtype, device, cfg):
+    from vit_prisma.b200.synthetic import recipe_state_dict
     from vit_prisma.configs.HookedViTConfig import HookedViTConfig
     from vit_prisma.models.base_vit import HookedViT
-    import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
-        model = HookedViT(HookedViTConfig(**(cfg or CLIP_B32), dtype=dtype))
+        model = HookedViT(HookedViTConfig(**cfg, dtype=dtype))
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     model.load_state_dict(recipe_state_dict(shapes, 1234))
     return model.to(device, dtype).eval()
@@ -240,6 +339,7 @@ def time_dominant_gemm(model, batch, dtype, iters=10):
     pre = torch.empty(M, N, device="cuda", dtype=dtype)
     post = torch.empty(M, N, device="cuda", dtype=dtype)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
     def call():
         ops.gemm(a, win, mlp.b_in, act=cfg.activation_name, a_lo=a_lo, w_lo=win_lo, out0=pre, out1=post)
     for _ in range(3):
@@ -256,15 +356,10 @@ def time_dominant_gemm(model, batch, dtype, iters=10):
     return {"ms": ms, "flops": 2.0 * M * N * K, "bytes": float(M * K * es + N * K * es + 2 * M * N * es), "shape": [M, N, K]}
 
 
-def run_ours(args):
-    world, rank, local = _dist()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    from oracle.vit_oracle import CLIP_B32, CLIP_L14
+def run_vit(args, ctx):
     from vit_prisma.b200 import _lib as L
+    from vit_prisma.b200.synthetic import CLIP_B32, CLIP_L14
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
     l14 = args.model == "l14"
     CFG = CLIP_L14 if l14 else CLIP_B32
@@ -277,27 +372,12 @@ def run_ours(args):
     x = host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        import torch.distributed as dist
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---- device-resident throughput
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(ctx.local)
     for _ in range(args.warmup):
         out, cache = model.run_with_cache(x, **run_kw)
         del cache
-    barrier()
+    ctx.barrier()
     n_keys = 0
     launches0 = L.get_lib().pb_launch_count()
     with clocks:
@@ -308,8 +388,8 @@ def run_ours(args):
             n_keys = len(cache)
             del cache
         e1.record()
-        barrier()
-        dev_ms = max_over_ranks(e0.elapsed_time(e1))
+        ctx.barrier()
+        dev_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     clocks.close()
     launches = L.get_lib().pb_launch_count() - launches0
     route = model.last_route
@@ -327,25 +407,22 @@ def run_ours(args):
         out, cache = model.run_with_cache(xd, **run_kw)
         out_host.copy_(result(out), non_blocking=True)
         del cache
-    barrier()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    marks = []
     for xd in loader.feed(host for _ in range(args.steps)):
         out, cache = model.run_with_cache(xd, **run_kw)
         out_host.copy_(result(out), non_blocking=True)
         del cache
-        if os.environ.get("PRISMA_BENCH_DEBUG"):
-            marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
     e1.record()
     del xd
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    if marks:
-        print("e2e per-step ms:", [round(a.elapsed_time(b), 2) for a, b in zip([e0] + marks[:-1], marks)], file=sys.stderr)
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
 
     if rank != 0:
-        return
+        del model, x, out
+        torch.cuda.empty_cache()
+        return None
     peaks = _peaks()
     imgs = world * B * args.steps
     value = imgs / (dev_ms / 1e3)
@@ -353,249 +430,356 @@ def run_ours(args):
     kern = time_dominant_gemm(model, B, dtype)
     flops_img = vit_flops_per_image(CFG, run_kw.get("stop_at_layer"))
     cache_b_img = (CFG["d_model"] * ((CFG["image_size"] // CFG["patch_size"]) ** 2 + 1) * 4) if l14 else 38_980_176   # fp32 bytes
+    fp32 = dtype == torch.float32
     # fp32 mode executes 3 tensor-core passes per algorithmic flop; the roofline counts ALGORITHMIC flops
     achieved = kern["flops"] / (kern["ms"] / 1e3) / 1e12
-    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from one `ncu --set full` capture (profiles/r01_gemm_fp32_ncu_summary.txt,
-    # profiles/r01_gemm_bf16_v3_ncu_summary.txt); algorithmic: A (+ lo plane) + weights read, two M x N outputs written
-    traffic = None if l14 else ((180.070400e6 + 580.768512e6) if dtype == torch.float32 else (44.133632e6 + 262.480640e6))
+    traffic, traffic_src = (None, None) if l14 else ncu_traffic(r"k_gemm_tc2<float" if fp32 else r"k_gemm_tc2<__nv_bfloat16|k_gemm_tc2<bf16",
+                                                                prefer="gemm_fp32" if fp32 else "gemm_bf16")
+    # the tensor core runs kind::tf32 at half the kind::f16 rate: the fp32-mode denominator is bf16_peak / 2 per executed pass,
+    # i.e. bf16_peak / 6 per algorithmic flop of the 3-pass product (MEASURED_PEAKS.json has no TF32 entry; derived, not measured)
+    mode_peak = peaks["bf16_tflops"] / 6 if fp32 else peaks["bf16_tflops"]
     roof = {"bound": "tensor", "kernel": "k_gemm_tc2 (MLP-in GEMM + bias + GELU, hook_pre/hook_post spill)", "achieved": achieved,
             "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-            "traffic_unit": "B/launch (ncu dram read+write)", "algorithmic_bytes": kern["bytes"],
-            "executed_tensor_tflops": achieved * (3 if dtype == torch.float32 else 1),
-            "note": ("fp32 = 3 TF32 passes per algorithmic flop at half the bf16 MMA rate: ncu shows the tensor pipe 71.5 % active "
-                     "on this launch (profiles/r01_gemm_fp32_ncu_summary.txt); frac is algorithmic flops over the bf16 peak") if dtype == torch.float32 else
-                    "ncu: tensor pipe 36.6 % active, issue slots 50.6 % (profiles/r01_gemm_bf16_v3_ncu_summary.txt)",
+            "traffic_source": traffic_src, "traffic_unit": "B/launch (ncu dram read+write)", "algorithmic_bytes": kern["bytes"],
+            "executed_tensor_tflops": achieved * (3 if fp32 else 1),
+            "mode_peak": mode_peak, "mode_frac": achieved / mode_peak,
+            "mode_peak_source": ("bf16_tflops / 2 (kind::tf32 runs at half the kind::f16 rate) / 3 passes -- derived from the measured bf16 peak"
+                                 if fp32 else "measured bf16 burst"),
             "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)", "shape_MNK": kern["shape"], "kernel_ms": kern["ms"],
             "hbm_gbs_of_kernel": kern["bytes"] / (kern["ms"] / 1e3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
-            "passes": 3 if dtype == torch.float32 else 1,
+            "passes": 3 if fp32 else 1,
             "step_algorithmic_tflops": flops_img * imgs / (dev_ms / 1e3) / 1e12,
-            "step_cache_write_gbs": cache_b_img * (1 if dtype == torch.float32 else 0.5) * imgs / (dev_ms / 1e3) / 1e9}
+            "step_mode_frac": flops_img * imgs / (dev_ms / 1e3) / 1e12 / (mode_peak if fp32 else (peaks["bf16_tflops_sustained"] or mode_peak)),
+            "step_cache_write_gbs": cache_b_img * (1 if fp32 else 0.5) * imgs / (dev_ms / 1e3) / 1e9}
     cpu = cpu_vit_images_per_sec(batch=4, cfg=CFG, layer=args.layer) if l14 else cpu_vit_images_per_sec()
-    es = 4 if dtype == torch.float32 else 2
-    metric = (f"run_with_cache images/sec (CLIP ViT-L/14, blocks.{args.layer}.hook_resid_post, stop_at_layer={args.layer + 1})" if l14
-              else "run_with_cache images/sec (CLIP ViT-B/32, all hook points cached)")
-    line = {"metric": metric, "value": value, "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"vit_l14_run_with_cache_resid_post_l{args.layer}" if l14 else "vit_b32_run_with_cache_all_hooks",
-                       "model": ("CLIP ViT-L/14" if l14 else "CLIP ViT-B/32") + " geometry, seeded synthetic weights",
-                       "batch_per_gpu": B, "global_batch": B * world, "hook_points_cached": n_keys, "route": route,
-                       "gemm": "tcgen05 3xTF32" if dtype == torch.float32 else "tcgen05 bf16",
-                       "cache_bytes_per_image": int(cache_b_img * es / 4), "l2": "working set (activations of one layer >> 126 MB) larger than L2",
-                       "parallelism": f"dp{world} (images sharded, no collective)"},
-            "clocks": clocks.summary(), "gpu_launches": int(launches),
-            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * host.element_size()),
-                    "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()), "ms_per_step": e2e_ms / args.steps,
-                    "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
-            "roofline": roof, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    es = 4 if fp32 else 2
+    rec = {"metric": vit_metric(l14, args.layer), "value": value, "unit": "images/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+           "config": {"workload": f"vit_l14_run_with_cache_resid_post_l{args.layer}" if l14 else "vit_b32_run_with_cache_all_hooks",
+                      "model": ("CLIP ViT-L/14" if l14 else "CLIP ViT-B/32") + " geometry, seeded synthetic weights",
+                      "batch_per_gpu": B, "global_batch": B * world, "hook_points_cached": n_keys, "route": route,
+                      "gemm": "tcgen05 3xTF32" if fp32 else "tcgen05 bf16",
+                      "cache_bytes_per_image": int(cache_b_img * es / 4), "l2": "working set (activations of one layer >> 126 MB) larger than L2",
+                      "parallelism": f"dp{world} (images sharded, no collective)"},
+           "clocks": clocks.summary(), "gpu_launches": int(launches),
+           "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * host.element_size()),
+                   "d2h_bytes_per_step": int(out_host.numel() * out_host.element_size()), "ms_per_step": e2e_ms / args.steps,
+                   "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
+           "roofline": roof, "cpu_baseline": cpu}
+    del model, x, out
+    torch.cuda.empty_cache()
+    return rec
 
 
-# ------------------------------------------------------------------ SAE workload (cfg #3: d=768, F=768*32, k=32, 4096 tokens/step, fp32)
-SAE_CFG = dict(d_in=768, expansion=32, k=32, batch=4096)
+# =====================================================================================================================
+# Path B: the SAE training step through VisionSAETrainer.train_step
+# =====================================================================================================================
+SAE_METRIC = "SAE training tokens/sec (TopK SAE, d_model=768, dict=768x32, k=32)"
 
 
-def sae_init_params(d, F, seed=0, device="cpu"):
-    g = torch.Generator().manual_seed(seed)
-    W_dec = torch.randn(F, d, generator=g)
-    W_dec /= W_dec.norm(dim=1, keepdim=True)
-    W_encT = torch.randn(F, d, generator=g)
-    W_encT /= W_encT.norm(dim=0, keepdim=True) + 1e-12      # reference: rows of W_enc [d,F] unit-norm
-    return dict(W_encT=W_encT.to(device), W_dec=W_dec.to(device), b_enc=torch.zeros(F, device=device), b_dec=torch.zeros(d, device=device))
+class _PoolStore:
+    """Activation store stand-in with the store's contract (``storage_buffer`` [tokens, n_layers, d_in], ``next_batch()``) over a
+    device-resident synthetic pool, served in fixed windows so the timed loops do no gather work of their own."""
+
+    def __init__(self, pool_dev, batch):
+        self.storage_buffer = pool_dev.unsqueeze(1)
+        self.batch, self.i = batch, 0
+
+    def window(self, i):
+        j = (i % (self.storage_buffer.shape[0] // self.batch)) * self.batch
+        return self.storage_buffer[j:j + self.batch]
+
+    def next_batch(self):
+        self.i += 1
+        return self.window(self.i - 1)
 
 
-def sae_pool(tokens, d, seed=0):
-    g = torch.Generator().manual_seed(seed)
-    off = torch.randn(d, generator=g)
-    return torch.randn(tokens, d, generator=g) * 2.0 + off
+def sae_runner_cfg(d, expansion, k, batch, lr=1e-3, **kw):
+    from vit_prisma.sae.config import VisionModelSAERunnerConfig
+    base = dict(d_in=d, expansion_factor=expansion, activation_fn_str="topk", activation_fn_kwargs={"k": k}, train_batch_size=batch, lr=lr,
+                lr_warm_up_steps=500, lr_scheduler_name="cosineannealingwarmup", max_grad_norm=1.0, normalize_activations="layer_norm",
+                b_dec_init_method="mean", initialization_method="independent", _device="cuda", _dtype="float32", n_checkpoints=0,
+                log_to_wandb=False, verbose=False, checkpoint_path="/tmp/prisma_b200_bench", hook_point_layer=9)
+    base.update(kw)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return VisionModelSAERunnerConfig(**base)
 
 
-def cpu_sae_tokens_per_sec(budget_s=12.0, threads=None, batch=1024):
-    """Oracle port of the reference train_step (dense autograd-equivalent formulas) on host cores, bounded sample."""
-    from oracle.sae_oracle import new_adam_state, sae_train_step
-    threads = threads or _cpu_cores()
-    torch.set_num_threads(threads)
-    d, F, k = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"], SAE_CFG["k"]
-    p0 = sae_init_params(d, F)
-    p = {"W_enc": p0["W_encT"].t().contiguous(), "W_dec": p0["W_dec"], "b_enc": p0["b_enc"], "b_dec": p0["b_dec"]}
-    state = new_adam_state(p)
-    x = sae_pool(batch, d)
-    sae_train_step(p, state, x, k, 1e-3, 1)
-    n, t0 = 0, time.perf_counter()
-    while True:
-        sae_train_step(p, state, x, k, 1e-3, n + 2)
-        n += 1
-        dt = time.perf_counter() - t0
-        if dt >= budget_s or n >= 16:
-            break
-    return {"value": n * batch / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
-            "sample": f"{n} train steps x {batch} tokens (of the 4096-token step), d=768 F=24576 k=32 fp32, oracle/sae_oracle.py, {dt:.1f}s"}
+def build_sae_trainer(ctx, cfg, store, group=None, init=None):
+    """VisionSAETrainer on ``store``; parameters from ``init`` (state-dict-shaped) or the seeded synthetic dictionary; for
+    world > 1 the trainer's own ``enable_data_parallel_if_requested`` moves them into NVLink peer-visible buffers."""
+    from vit_prisma.b200.synthetic import sae_init_params
+    from vit_prisma.sae.train_sae import VisionSAETrainer
+    with contextlib.redirect_stdout(io.StringIO()):
+        trainer = VisionSAETrainer(cfg, model=None, dataset=None, activations_store=store, p2p_group=group)
+    sae = trainer.sparse_coder
+    if init is None:
+        p = sae_init_params(cfg.d_in, int(cfg.d_sae), device=ctx.dev)
+        init = {"W_enc": p["W_encT"].t(), "W_dec": p["W_dec"], "b_enc": p["b_enc"], "b_dec": p["b_dec"]}
+    with torch.no_grad():
+        wt, wd, be, bd = sae._canonical_params()
+        wt.copy_(init["W_enc"].t().to(ctx.dev))
+        wd.copy_(init["W_dec"].to(ctx.dev))
+        be.copy_(init["b_enc"].to(ctx.dev))
+        bd.copy_(init["b_dec"].to(ctx.dev))
+    return trainer
 
 
-def run_sae(args):
-    world, rank, local = _dist()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+def run_sae(args, ctx):
     from vit_prisma.b200 import _lib as L
-    from vit_prisma.b200.sae_engine import SaeStepEngine, unit_norm_rows_
+    from vit_prisma.b200.synthetic import activation_pool
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     d, F, k, Bt = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"], SAE_CFG["k"], SAE_CFG["batch"]
-    p = sae_init_params(d, F, device=dev)
+    cfg = sae_runner_cfg(d, SAE_CFG["expansion"], k, Bt)
+    pool_host = activation_pool(Bt * POOL_BATCHES, d, seed=rank).pin_memory()        # every rank: its own token shard
+    store = _PoolStore(pool_host.to(dev), Bt)
+    group = None
     if world > 1:      # data parallel over NVLink peer memory: Bt tokens per GPU, one global step (csrc/p2p.cu)
-        from vit_prisma.b200.p2p import P2PGroup, SaeDPEngine
-        eng = SaeDPEngine(P2PGroup(rank, world, dev), p["W_encT"], p["W_dec"], p["b_enc"], p["b_dec"], k=k)
-    else:
-        eng = SaeStepEngine(p["W_encT"], p["W_dec"], p["b_enc"], p["b_dec"], k=k)
-    unit_norm_rows_(eng.W_dec)
-    eng.refresh_lo()
-    pool_host = sae_pool(Bt * 16, d, seed=rank).pin_memory()
-    pool = pool_host.to(dev)
-    eng.b_dec.copy_(sae_pool(Bt * 16, d, seed=0).mean(0).to(dev))     # identical b_dec init on every rank
-    since_fired, act_freq = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
-    lr = 1e-3
+        from vit_prisma.b200.p2p import P2PGroup
+        group = P2PGroup(rank, world, dev)
+    trainer = build_sae_trainer(ctx, cfg, store, group)
+    sae = trainer.sparse_coder
+    act_freq, since_fired, n_frac, optimizer, scheduler = trainer.initialize_training_variables()
+    trainer.initialize_geometric_medians()               # b_dec = mean of the store's buffer (rank 0's is broadcast below)
+    trainer.enable_data_parallel_if_requested()
+    eng = sae.step_engine()
+    if world > 1:
+        from vit_prisma.b200.p2p import SaeDPEngine
+        assert isinstance(eng, SaeDPEngine), "trainer did not keep the data-parallel engine"
+    state = {"step": 0, "tokens": 0, "n_frac": n_frac}
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step(layer_acts):
+        out = trainer.train_step(sparse_autoencoder=sae, optimizer=optimizer, scheduler=scheduler, act_freq_scores=act_freq,
+                                 n_forward_passes_since_fired=since_fired, n_frac_active_tokens=state["n_frac"], layer_acts=layer_acts,
+                                 n_training_steps=state["step"], n_training_tokens=state["tokens"])
+        state["step"] += 1
+        state["tokens"] += Bt * world
+        state["n_frac"] = out[-1]
+        return out[0]                                     # loss: 0-dim device tensor
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        import torch.distributed as dist
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def batch(i):
-        j = (i % 16) * Bt
-        return pool[j:j + Bt]
-
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(ctx.local, period_s=0.002)
     for i in range(args.warmup):
-        eng.train_step(batch(i), lr, since_fired, act_freq)
-    barrier()
+        step(store.window(i))
+    ctx.barrier()
     l0 = L.get_lib().pb_launch_count()
     with clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t_host = time.perf_counter()
         for i in range(args.steps):
-            eng.train_step(batch(i), lr, since_fired, act_freq)
+            step(store.window(args.warmup + i))
         e1.record()
         host_enqueue_ms = 1e3 * (time.perf_counter() - t_host) / args.steps
-        barrier()
-        dev_ms = max_over_ranks(e0.elapsed_time(e1))
+        ctx.barrier()
+        dev_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     clocks.close()
     launches = L.get_lib().pb_launch_count() - l0
-    # e2e: pinned host tokens -> H2D -> step -> D2H of the step scalars (mse, l0, grad norm, ...)
-    sc_host = torch.empty(8).pin_memory()
+    assert sae.step_engine() is eng, "the step engine was rebuilt during training"
+
+    # ---- e2e: pinned host tokens -> H2D -> VisionSAETrainer.train_step -> D2H of the step's loss
+    loss_host = torch.empty(1).pin_memory()
     from vit_prisma.b200.prefetch import DevicePrefetcher
-    host_batches = lambda n: (pool_host[(i % 16) * Bt:(i % 16 + 1) * Bt] for i in range(n))
+    host_batches = lambda n: (pool_host[(i % POOL_BATCHES) * Bt:(i % POOL_BATCHES + 1) * Bt].unsqueeze(1) for i in range(n))  # noqa: E731
     loader = DevicePrefetcher(None, dev)
     for xin in loader.feed(host_batches(max(3, args.warmup))):
-        sc_host.copy_(eng.train_step(xin, lr, since_fired, act_freq), non_blocking=True)
-    barrier()
+        loss_host.copy_(step(xin).reshape(1), non_blocking=True)
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host = time.perf_counter()
     for xin in loader.feed(host_batches(args.steps)):
-        sc_host.copy_(eng.train_step(xin, lr, since_fired, act_freq), non_blocking=True)
+        loss_host.copy_(step(xin).reshape(1), non_blocking=True)
     e1.record()
     e2e_host_ms = 1e3 * (time.perf_counter() - t_host) / args.steps
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    final_loss = float(loss_host.item())
+    # ---- per-stage device times (instrumented replays of one step's stages, warm) -> which kernel dominates.
+    # Collective under data parallelism (the peer-memory phases contain barriers), so every rank runs it.
+    stages = eng.time_stages(store.window(0)[:, 0, :].contiguous(), float(optimizer.param_groups[0]["lr"]), since_fired, act_freq)
+    ctx.barrier()
     if rank != 0:
-        return
-    # per-stage device times (one extra instrumented step) -> dominant kernel for the roofline
-    import ctypes as C
-    lib, st = L.get_lib(), torch.cuda.current_stream().cuda_stream
-    stages = {}
-
-    def timed(name, fn, reps=5):
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        stages[name] = a.elapsed_time(b) / reps
-
-    x = batch(0).contiguous()
-    timed("encode_topk (prep + encoder GEMM 3xTF32 + topk)", lambda: eng.encode_topk(x))
-    eng.scalars.zero_(); eng.step_count += 1
-    s = eng._desc(x, training=True, lr=lr, since_fired=since_fired, act_freq=act_freq, want_out=False)
-    timed("decode (sparse decode + loss + d_hidden)", lambda: L.check(lib.pb_sae_decode(C.byref(s), st)))
-    timed("backward (csc + per-feature grads + norm)", lambda: (eng.scalars.zero_(), L.check(lib.pb_sae_backward(C.byref(s), st))))
-    timed("adam (clip + projection + Adam + renorm)", lambda: L.check(lib.pb_sae_adam(C.byref(s), st)))
+        return None
     peaks = _peaks()
     tokens = world * Bt * args.steps
     value = tokens / (dev_ms / 1e3)
+    ms_step = dev_ms / args.steps
     step_bytes = eng.algorithmic_bytes(Bt)
-    timed("encoder GEMM alone (hidden_pre = sae_in @ W_enc + b_enc, 3xTF32)", lambda: eng._encoder_gemm(Bt))
-    adam_bytes = 60 * d * F            # per matrix element pair: g,p,m,v read (16 B) + p,m,v write (12 B) (x2) + tf32 residual write (4 B)
-    adam_gbs = adam_bytes / (stages["adam (clip + projection + Adam + renorm)"] / 1e3) / 1e9
-    gemm_ms = stages["encoder GEMM alone (hidden_pre = sae_in @ W_enc + b_enc, 3xTF32)"]
-    gemm_tflops = 2.0 * Bt * d * F / (gemm_ms / 1e3) / 1e12
-    # dominant kernel of the step (41 % of the launch time, profiles/r01_launches_sae_v2.txt): the fp32-grade encoder GEMM.
-    # The step as a whole is the HBM-bound object SURVEY 8d describes; its bytes and the Adam kernel's are reported beside it.
-    roof = {"bound": "tensor", "kernel": "k_gemm_tc2<float,3,128,3,4> (encoder GEMM, 3 TF32 passes, m-fastest raster)", "achieved": gemm_tflops,
-            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": None,
-            "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)", "kernel_ms": gemm_ms, "passes": 3,
-            "executed_tensor_tflops": 3 * gemm_tflops, "shape_MNK": [Bt, F, d],
-            "hbm_kernel": {"kernel": "k_sae_adam_rows (clip + decoder-parallel-grad removal + Adam + row renorm)", "achieved": adam_gbs,
-                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": adam_gbs / peaks["hbm_gbs"],
-                           "algorithmic_bytes_per_launch": adam_bytes, "traffic": 604.774912e6 + 474.265088e6,
-                           "traffic_source": "ncu dram read+write, profiles/r01_sae_step_ncu_summary.txt"},
-            "step_algorithmic_bytes": step_bytes, "step_hbm_gbs": step_bytes / (dev_ms / args.steps / 1e3) / 1e9,
-            "step_hbm_frac": step_bytes / (dev_ms / args.steps / 1e3) / 1e9 / peaks["hbm_gbs"], "stage_ms": stages}
+    step_gbs = step_bytes / (ms_step / 1e3) / 1e9
+    kernels = []
+    for name, info in stages.items():
+        ent = {"stage": name, "ms": info["ms"]}
+        if info.get("bytes"):
+            ent.update(algorithmic_bytes=info["bytes"], achieved_gbs=info["bytes"] / (info["ms"] / 1e3) / 1e9,
+                       hbm_frac=info["bytes"] / (info["ms"] / 1e3) / 1e9 / peaks["hbm_gbs"])
+        if info.get("flops"):
+            ent.update(algorithmic_flops=info["flops"], achieved_tflops=info["flops"] / (info["ms"] / 1e3) / 1e12,
+                       passes=info.get("passes", 1))
+        if info.get("nvlink_bytes"):
+            ent.update(nvlink_bytes=info["nvlink_bytes"], nvlink_gbs=info["nvlink_bytes"] / (info["ms"] / 1e3) / 1e9)
+        if info.get("ncu") and "alone" not in name:
+            t, src = ncu_traffic(info["ncu"], prefer="sae")
+            ent.update(traffic=t, traffic_source=src)
+        kernels.append(ent)
+    kernels.sort(key=lambda e: -e["ms"])
+    dom = kernels[0]
+    with_ncu = [e for e in kernels if "traffic" in e]
+    traffic_total = sum(e["traffic"] for e in with_ncu) if with_ncu and all(e["traffic"] is not None for e in with_ncu) else None
+    roof = {"bound": "hbm", "kernel": "whole training step (SURVEY 8d: 80 d F + 8 Bt d algorithmic bytes; weights + gradients + Adam state dominate)",
+            "achieved": step_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_gbs / peaks["hbm_gbs"],
+            "traffic": traffic_total, "traffic_unit": "B/step (sum of the stages' ncu dram read+write, committed summaries under profiles/)",
+            "algorithmic_bytes": step_bytes, "peak_source": peaks["source"] + " HBM copy bandwidth",
+            "dominant_kernel": dom, "stages": kernels}
     cpu = cpu_sae_tokens_per_sec()
-    line = {"metric": "SAE training tokens/sec (TopK SAE, d_model=768, dict=768x32, k=32)", "value": value, "unit": "tokens/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "sae_topk_train_step", "d_in": d, "d_sae": F, "k": k, "tokens_per_step_per_gpu": Bt,
-                       "encoder_gemm": "tcgen05 3xTF32", "normalize_activations": "layer_norm", "max_grad_norm": 1.0,
-                       "l2": "working set (2 x 75 MB weights + 2 x 150 MB Adam state + 150 MB grads + 403 MB hidden_pre) larger than L2",
-                       "parallelism": f"dp{world}" + (" (NVLink peer-memory reduce-scatter + sharded Adam + all-gather, no NCCL on the data path; "
-                                                       f"{int((world - 1) / world * (2 * d * F * 4 * 2 + d * F * 4) / 1e6)} MB over NVLink per GPU per step)" if world > 1 else "")},
-            "clocks": clocks.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
-            "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * 4, "d2h_bytes_per_step": 32,
-                    "ms_per_step": e2e_ms / args.steps, "host_enqueue_ms_per_step": e2e_host_ms,
-                    "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
-            "roofline": roof, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    nvlink_mb = int((world - 1) / world * (2 * d * F * 4 * 2 + d * F * 4) / 1e6)
+    rec = {"metric": SAE_METRIC, "value": value, "unit": "tokens/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "config": {"workload": "sae_topk_train_step", "api": "VisionSAETrainer.train_step", "d_in": d, "d_sae": F, "k": k,
+                      "tokens_per_step_per_gpu": Bt, "global_batch": Bt * world, "engine": type(eng).__name__,
+                      "encoder": eng.describe_encoder(), "normalize_activations": "layer_norm", "max_grad_norm": 1.0,
+                      "l2": "working set (2 x 75 MB weights + 2 x 150 MB Adam state + 150 MB gradients + 201 MB activation pool) larger than L2",
+                      "parallelism": f"dp{world}" + (" (NVLink peer-memory reduce-scatter + sharded Adam + all-gather, no NCCL on the data path; "
+                                                      f"{nvlink_mb} MB over NVLink per GPU per step)" if world > 1 else "")},
+           "clocks": clocks.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
+           "final_loss": final_loss,
+           "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * 4, "d2h_bytes_per_step": 4,
+                   "ms_per_step": e2e_ms / args.steps, "host_enqueue_ms_per_step": e2e_host_ms,
+                   "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
+           "roofline": roof, "cpu_baseline": cpu}
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def dp_parity_gate(ctx):
+    """N > 1 only, after the timed regions: the NVLink data-parallel step, driven through VisionSAETrainer(p2p_group=...), must
+    reproduce the reference's single-process training of tests/golden/sae_tiny_b.pt (fixture made by the unmodified reference):
+    global mse, grad norm, bit-exact TopK indices, parameters after steps 0 / 2 / 5, dead-feature counters, and identical
+    parameters on every rank.  Returns (ok, detail) on every rank."""
+    import torch.distributed as dist
+    from vit_prisma.b200.p2p import P2PGroup, SaeDPEngine
+    from vit_prisma.sae.train_sae import FusedAdamHandle, FusedSchedule
+    from vit_prisma.sae.training.get_scheduler import lr_multiplier_fn
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "sae_tiny_b.pt"), weights_only=False)
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    B, d, k, F = gold["batch"], gold["d_in"], gold["k"], gold["d_sae"]
+    g = torch.Generator().manual_seed(gold["data_seed"])
+    data = torch.randn(B * gold["n_steps"], d, generator=g) * 2.0 + torch.randn(d, generator=g)
+    if B % world or F % world:
+        return True, f"skipped: batch {B} / d_sae {F} not divisible by {world}"
+    per = B // world
+    cfg = sae_runner_cfg(d, F // d, k, per, lr=gold["lr"], normalize_activations=gold["norm"], b_dec_init_method="zeros")
+    trainer = build_sae_trainer(ctx, cfg, store=None, group=P2PGroup(rank, world, dev), init=gold["init"])
+    trainer.enable_data_parallel_if_requested()
+    sae = trainer.sparse_coder
+    eng = sae.step_engine()
+    problems = []
+    if not isinstance(eng, SaeDPEngine):
+        problems.append(f"step_engine() returned {type(eng).__name__}, not SaeDPEngine")
+    since_fired, act_freq = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
+    optimizer = FusedAdamHandle(gold["lr"])
+    scheduler = FusedSchedule(optimizer, gold["lr"], lr_multiplier_fn("cosineannealingwarmup", warm_up_steps=gold["warm_up_steps"],
+                                                                      training_steps=gold["total_steps"], lr_end=gold["lr_end"]))
+    n_frac, worst = 0, 0.0
+    rel = lambda got, want: float((got.double().cpu() - want.double()).abs().max() / max(float(want.double().abs().max()), 1e-30))  # noqa: E731
+    for s, rec in enumerate(gold["steps"]):
+        x = data[s * B + rank * per: s * B + (rank + 1) * per].to(dev).unsqueeze(1)
+        out = trainer.train_step(sparse_autoencoder=sae, optimizer=optimizer, scheduler=scheduler, act_freq_scores=act_freq,
+                                 n_forward_passes_since_fired=since_fired, n_frac_active_tokens=n_frac, layer_acts=x,
+                                 n_training_steps=s, n_training_tokens=s * B)
+        n_frac = out[-1]
+        torch.cuda.synchronize()
+        if sae.step_engine() is not eng:
+            problems.append(f"step {s}: the trainer rebuilt the step engine")
+            eng = sae.step_engine()
+        sc = eng.scalars_dict()
+        mse = torch.tensor([sc["mse"]], device=dev)
+        dist.all_reduce(mse)                                 # shares of the global mean add up
+        if abs(mse.item() - rec["mse"]) > 1e-4 * abs(rec["mse"]):
+            problems.append(f"step {s}: mse {mse.item():.6g} vs reference {rec['mse']:.6g}")
+        if abs(sc["grad_norm"] - rec["grad_norm"]) > 1e-4 * rec["grad_norm"]:
+            problems.append(f"step {s}: grad norm {sc['grad_norm']:.6g} vs reference {rec['grad_norm']:.6g}")
+        if not torch.equal(eng.idx.cpu().long(), rec["topk_idx"][rank * per:(rank + 1) * per]):
+            problems.append(f"step {s}: TopK indices differ from the reference")
+        if "params_after" in rec:
+            ref = rec["params_after"]
+            ref_dec = ref["W_dec"] / ref["W_dec"].norm(dim=1, keepdim=True)
+            sd = sae.state_dict()
+            for name, got, want in (("W_dec", sd["W_dec"], ref_dec), ("W_enc", sd["W_enc"], ref["W_enc"]), ("b_enc", sd["b_enc"], ref["b_enc"]),
+                                    ("b_dec", sd["b_dec"], ref["b_dec"])):
+                e = rel(got, want)
+                worst = max(worst, e)
+                if e > 1e-4:
+                    problems.append(f"step {s}: {name} rel err {e:.2e}")
+    if not (torch.equal(since_fired.cpu(), gold["since_fired"]) and torch.equal(act_freq.cpu(), gold["act_freq"])):
+        problems.append("dead-feature counters differ from the reference")
+    # every rank must hold bit-identical parameters
+    sd = sae.state_dict()
+    sig = torch.stack([sd[n].double().sum() for n in ("W_enc", "W_dec", "b_enc", "b_dec")] +
+                      [sd[n].double().abs().sum() for n in ("W_enc", "W_dec")]).to(dev)
+    lo, hi = sig.clone(), sig.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if not torch.equal(lo, hi):
+        problems.append("parameters differ between ranks after training")
+    flag = torch.tensor([0.0 if problems else 1.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if problems:
+        print(f"[dp_parity rank {rank}] " + "; ".join(problems), file=sys.stderr, flush=True)
+    return bool(flag.item() == 1.0), {"fixture": "tests/golden/sae_tiny_b.pt (unmodified reference, single process)", "world": world,
+                                      "steps": len(gold["steps"]), "worst_param_rel_err": worst, "api": "VisionSAETrainer(p2p_group=...).train_step",
+                                      "problems_rank0": problems}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vit", choices=["vit", "sae"])
-    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
-    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--workload", default="all", choices=["all", "sae", "vit"],
+                    help="all (default) = SAE training step as the headline record + the full run_with_cache record under 'secondary'")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="ViT model dtype (the SAE step is fp32)")
+    ap.add_argument("--batch", type=int, default=512, help="ViT images per step per GPU")
     ap.add_argument("--model", default="b32", choices=["b32", "l14"], help="l14 = cfg #4: ViT-L/14 with the activation store's names_filter / stop_at_layer")
     ap.add_argument("--layer", type=int, default=22, help="hook_resid_post layer cached by --model l14")
+    ap.add_argument("--vit-steps", type=int, default=None, help="steps of the secondary ViT record under --workload all (default: min(steps, 10))")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    ctx = Ctx()
+    rc = 0
     try:
-        if args.workload == "sae":
-            return run_sae(args)
-        run_ours(args)
+        line = None
+        if args.workload in ("all", "sae"):
+            line = run_sae(args, ctx)
+            if ctx.world > 1:
+                ok, detail = dp_parity_gate(ctx)
+                if line is not None:
+                    line["dp_parity"], line["dp_parity_detail"] = ok, detail
+                rc = 0 if ok else 3
+        if args.workload in ("all", "vit"):
+            vargs = argparse.Namespace(**vars(args))
+            if args.workload == "all":
+                vargs.steps = args.vit_steps or min(args.steps, 10)
+                vargs.warmup = min(args.warmup, 3)
+            vit = run_vit(vargs, ctx)
+            if args.workload == "vit":
+                line = vit
+            elif line is not None:
+                line["secondary"] = vit
+        if ctx.rank == 0 and line is not None:
+            print(json.dumps(line), flush=True)
     finally:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             dist.barrier()
             dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 if __name__ == "__main__":

@@ -2,6 +2,7 @@
 shards of ``[tokens, n_layers, d_in]`` -- writer, buffer loader and the cache-backed store, on CPU with a stand-in model."""
 import os
 
+import pytest
 import torch
 from torch.utils.data import TensorDataset
 
@@ -48,8 +49,13 @@ def test_writer_loader_and_cache_store_round_trip(tmp_path):
     buf = store._load_cached_activations(total_size=10, context_size=T, num_layers=1, d_in=D)
     assert buf.dtype == torch.float32 and torch.equal(buf, expect.float())
     assert store._load_cached_activations(total_size=3, context_size=T, num_layers=1, d_in=D).shape == (15, 1, D)
-    # the cache-backed store serves shuffled batches file by file and wraps around
+    # the cache-backed store: reference half-buffer mixing (activations_store.py:21-152) over the shards, wrapping around
+    with pytest.raises(ValueError):
+        CacheVisionActivationStore(cfg)                                       # reference :36-37
+    cfg.use_cached_activations = True
     cached = CacheVisionActivationStore(cfg)
+    half_tokens = (cfg.n_batches_in_buffer // 2) * cfg.store_batch_size * cfg.context_size
+    assert cached.storage_buffer.shape == (half_tokens, 1, D)                # kept half of a (fresh half + stored half) mix
     seen = []
     for _ in range(12):
         b = cached.next_batch()
@@ -58,7 +64,29 @@ def test_writer_loader_and_cache_store_round_trip(tmp_path):
     got = torch.cat(seen)
     rows = {tuple(r.flatten().tolist()) for r in expect.float()}
     assert all(tuple(r.flatten().tolist()) in rows for r in got)
-    assert cached.next_cache_idx >= 1
+    assert cached._file_idx >= 1 or cached._file_off > 0                      # the file cursor persists across refills
+
+
+def test_trainer_b_dec_init_reads_the_cache_store_buffer(tmp_path):
+    """VisionSAETrainer.initialize_geometric_medians() with a cache-backed store (mean / zeros / geometric_median)."""
+    from vit_prisma.sae.train_sae import VisionSAETrainer
+    images = torch.arange(10, dtype=torch.float32)[:, None, None, None].expand(10, 3, 4, 4).contiguous()
+    cfg = _cfg(tmp_path)
+    VisionActivationsStore(cfg, _FakeViT(), TensorDataset(images, torch.zeros(10, dtype=torch.long)),
+                           create_dataloader=False).generate_cached_activations_from_dataset(tokens_per_file=16)
+    for method in ("zeros", "mean", "geometric_median"):
+        cfg2 = _cfg(tmp_path, use_cached_activations=True, b_dec_init_method=method, activation_fn_str="topk", activation_fn_kwargs={"k": 2})
+        trainer = VisionSAETrainer(cfg2, model=None, dataset=None)
+        assert isinstance(trainer.activations_store, CacheVisionActivationStore)
+        trainer.initialize_geometric_medians()
+        b = trainer.sparse_coder.b_dec.detach()
+        buf = trainer.activations_store.storage_buffer[:, 0, :].float()
+        if method == "zeros":
+            assert torch.count_nonzero(b) == 0
+        elif method == "mean":
+            assert torch.allclose(b.float().cpu(), buf.mean(0).cpu(), atol=1e-6)
+        else:
+            assert torch.isfinite(b).all() and (b.float().cpu() - buf.mean(0).cpu()).abs().max() < buf.abs().max()
 
 
 def test_patches_only_drops_the_class_token(tmp_path):

@@ -196,3 +196,14 @@ def test_c_abi_struct_layouts_match_the_compiled_library():
             continue
         assert lib.pb_abi_sizeof(idx) == ctypes.sizeof(struct), struct.__name__
     assert lib.pb_abi_sizeof(10_000) == -1
+
+
+def test_product_synthetic_recipe_equals_the_oracle_recipe():
+    """bench.py / smoke() build product models from vit_prisma.b200.synthetic; the CPU checker restates the same recipe in oracle/."""
+    from oracle import vit_oracle
+    from vit_prisma.b200 import synthetic
+    assert synthetic.CLIP_B32 == vit_oracle.CLIP_B32 and synthetic.CLIP_L14 == vit_oracle.CLIP_L14
+    tiny = dict(vit_oracle.CLIP_B32, n_layers=1, d_model=16, d_head=8, n_heads=2, d_mlp=32, patch_size=16, image_size=32, n_classes=5)
+    shapes = vit_oracle.state_dict_shapes(tiny)
+    a, b = synthetic.recipe_state_dict(shapes, 99), vit_oracle.recipe_state_dict(shapes, 99)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)

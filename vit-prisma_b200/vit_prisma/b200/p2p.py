@@ -123,6 +123,7 @@ class P2PGroup:
 
 class SaeDPEngine(SaeStepEngine):
     """``SaeStepEngine`` whose optimizer step is the NVLink reduce-scatter / sharded Adam / all-gather of csrc/p2p.cu."""
+    is_data_parallel = True
 
     def __init__(self, group: P2PGroup, W_encT: torch.Tensor, W_dec: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, k: int, **kw):
         self.group = group
@@ -169,6 +170,10 @@ class SaeDPEngine(SaeStepEngine):
         lib, st, g = L.get_lib(), _stream(), self.group
         x = x.contiguous().float()
         rows = x.shape[0]
+        if getattr(self, "_dp_rows", rows) != rows:
+            raise L.PrismaB200Error(f"SaeDPEngine: every step (and every rank) must bring the same number of rows (had {self._dp_rows}, got {rows}); "
+                                    "drop or pad short batches before the data-parallel step")
+        self._dp_rows = rows
         # prep writes THIS rank's column sums of x into the shared xsum; decode needs the GLOBAL sums
         xsum_global, self.xsum = self.xsum, self.xsum_local
         self.encode_topk(x)
@@ -188,3 +193,25 @@ class SaeDPEngine(SaeStepEngine):
         L.check(lib.pb_p2p_adam_allgather(C.byref(ps), st), "pb_p2p_adam_allgather")
         g.barrier(ps)                                   # every rank holds the updated parameters
         return self.scalars
+
+    # ------------------------------------------------------------------ instrumentation: COLLECTIVE (every rank must call it)
+    def _prepare_timed_step(self, s: PbSaeStep, x: torch.Tensor) -> None:
+        s.global_rows, s.dist = x.shape[0] * self.group.world, 1
+
+    def _optimizer_stages(self, s: PbSaeStep, x: torch.Tensor, lr: float, since_fired, act_freq):
+        lib, st, g = L.get_lib(), _stream(), self.group
+        ps = self._p2p_desc(x.shape[0], lr, since_fired, act_freq)
+        n = self.group.world
+        link = (n - 1) / n * 8 * self.d * self.F          # bytes pulled over NVLink per rank: both gradient matrices, (N-1)/N of the owned slice x N peers
+
+        def rs():
+            g.barrier(ps)
+            L.check(lib.pb_p2p_reduce_scatter(C.byref(ps), st), "pb_p2p_reduce_scatter")
+
+        def adam():
+            g.barrier(ps)
+            L.check(lib.pb_p2p_adam_allgather(C.byref(ps), st), "pb_p2p_adam_allgather")
+            g.barrier(ps)
+        return [("p2p barrier + reduce-scatter (peer loads over NVLink)", rs, dict(nvlink_bytes=link, ncu=r"k_p2p_reduce_scatter")),
+                ("p2p barrier + sharded Adam + all-gather (peer stores) + barrier", adam,
+                 dict(bytes=60 * self.d * self.F // n, nvlink_bytes=(n - 1) / n * 12 * self.d * self.F, ncu=r"k_p2p_adam_allgather"))]

@@ -113,6 +113,7 @@ def sae_mse(x2: torch.Tensor, out2: torch.Tensor) -> torch.Tensor:
 
 class SaeStepEngine:
     """Buffers + launch sequence for one (d, F, k, rows) geometry.  ``train_step`` mutates the parameters in place."""
+    is_data_parallel = False
 
     def __init__(self, W_encT: torch.Tensor, W_dec: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, k: int,
                  normalize_activations: str = "layer_norm", max_grad_norm: float = 1.0, betas=(0.9, 0.999), adam_eps: float = 1e-8,
@@ -241,6 +242,61 @@ class SaeStepEngine:
         L.check(lib.pb_sae_backward(C.byref(s), st), "pb_sae_backward")
         L.check(lib.pb_sae_adam(C.byref(s), st), "pb_sae_adam")
         return self.scalars
+
+    # ------------------------------------------------------------------ instrumentation (bench.py / tools)
+    def describe_encoder(self) -> str:
+        return "tcgen05 3xTF32 GEMM -> dense hidden_pre -> exact k_topk" if self.gemm_impl != L.GEMM_SIMT else "exact FFMA GEMM -> k_topk"
+
+    def _optimizer_stages(self, s: PbSaeStep, x: torch.Tensor, lr: float, since_fired, act_freq):
+        """(name, callable, info) of the stages after backward; the data-parallel engine replaces them with its peer-memory phases."""
+        lib, st = L.get_lib(), _stream()
+        return [("adam (clip + decoder-parallel-gradient removal + Adam + row renorm)", lambda: L.check(lib.pb_sae_adam(C.byref(s), st)),
+                 dict(bytes=60 * self.d * self.F, ncu=r"k_sae_adam_rows"))]
+
+    @torch.no_grad()
+    def time_stages(self, x: torch.Tensor, lr: float, since_fired=None, act_freq=None, reps: int = 5) -> dict:
+        """CUDA-event time of every stage of one training step, each replayed ``reps`` times back to back on the current stream
+        (warm caches: shares of the step, not cold-start figures).  Mutates parameters / optimizer state like ``reps`` extra steps.
+        Returns ``{stage: {"ms", "bytes" | "flops" (algorithmic, per launch), "ncu" (kernel-name regex for profiles/)}}``."""
+        lib, st = L.get_lib(), _stream()
+        x = x.contiguous().float()
+        rows = x.shape[0]
+        out = {}
+
+        def timed(name, fn, **info):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            out[name] = dict(ms=a.elapsed_time(b) / reps, **info)
+
+        for name, fn, info in self._encode_stages(x):
+            timed(name, fn, **info)
+        self.encode_topk(x)
+        self.scalars.zero_()
+        self.step_count += 1
+        s = self._desc(x, training=True, lr=float(lr), since_fired=since_fired, act_freq=act_freq, want_out=False)
+        self._prepare_timed_step(s, x)
+        timed("decode (sparse decode + loss + d_hidden)", lambda: L.check(lib.pb_sae_decode(C.byref(s), st)),
+              bytes=(12 * rows * self.d + 8 * rows * self.k), ncu=r"k_sae_decode")
+        timed("backward (csc build + per-feature gradients + norm)", lambda: (self.scalars.zero_(), L.check(lib.pb_sae_backward(C.byref(s), st))),
+              bytes=8 * self.d * self.F, ncu=r"k_sae_grads<")
+        for name, fn, info in self._optimizer_stages(s, x, float(lr), since_fired, act_freq):
+            timed(name, fn, **info)
+        return out
+
+    def _prepare_timed_step(self, s: PbSaeStep, x: torch.Tensor) -> None:
+        pass
+
+    def _encode_stages(self, x: torch.Tensor):
+        rows = x.shape[0]
+        return [("encode + topk (prep + encoder GEMM 3xTF32 + exact topk)", lambda: self.encode_topk(x),
+                 dict(flops=2.0 * rows * self.d * self.F, passes=3, ncu=r"k_gemm_tc2<float")),
+                ("encoder GEMM alone (hidden_pre = sae_in @ W_enc + b_enc)", lambda: self._encoder_gemm(rows),
+                 dict(flops=2.0 * rows * self.d * self.F, passes=3, bytes=8 * self.d * self.F + 8 * rows * self.d + 4 * rows * self.F))]
 
     def dense_feature_acts(self) -> torch.Tensor:
         """feature_acts [rows, F] of the last encode (zeros.scatter_(idx, relu(val)))."""

@@ -171,31 +171,59 @@ class SparseAutoencoder(HookedRootModule, ABC):
             raise ValueError(f"Unexpected file extension: {path}, supported extensions are .pt and .pkl.gz")
         print(f"Saved SAE to {path}")
 
+    @staticmethod
+    def _read_checkpoint(weights_path: str):
+        readers = ((".pt", lambda p: torch.load(p, map_location="cpu", weights_only=False)),
+                   (".pkl.gz", lambda p: pickle.load(gzip.open(p, "rb"))),
+                   (".pkl", lambda p: pickle.load(open(p, "rb"))))
+        for suffix, read in readers:
+            if weights_path.endswith(suffix):
+                try:
+                    return read(weights_path)
+                except Exception as e:
+                    raise IOError(f"Error loading the state dictionary from {suffix} file: {e}")
+        raise ValueError(f"Unexpected file extension: {weights_path}, supported extensions are .pt, .pkl, and .pkl.gz")
+
     @classmethod
     def load_from_pretrained(cls, weights_path: str, current_cfg=None, config_path: Optional[str] = None):
+        """Reference sae/sae.py:409-523.  Accepts (a) a combined ``{"cfg", "state_dict"}`` checkpoint (what ``save_model`` writes),
+        (b) a weights-only file with ``config.json`` next to it (or ``config_path``).  ``current_cfg`` is a mapping of overrides
+        applied to fields the loaded config already has.  The class is chosen from the loaded config's ``architecture`` /
+        ``is_transcoder``, so the canonical call ``SparseAutoencoder.load_from_pretrained(path)`` works on the abstract base."""
         if not os.path.isfile(weights_path):
-            raise FileNotFoundError(f"No file found at specified path: {weights_path}")
-        if weights_path.endswith(".pt"):
-            payload = torch.load(weights_path, map_location="cpu", weights_only=False)
-        elif weights_path.endswith(".pkl.gz"):
-            with gzip.open(weights_path, "rb") as f:
-                payload = pickle.load(f)
-        elif weights_path.endswith(".pkl"):
-            with open(weights_path, "rb") as f:
-                payload = pickle.load(f)
+            raise FileNotFoundError(f"No weights file found at: {weights_path}")
+        payload = cls._read_checkpoint(weights_path)
+        combined = isinstance(payload, dict) and "cfg" in payload and "state_dict" in payload
+        if combined and config_path is None:
+            loaded_cfg, weights = payload["cfg"], payload["state_dict"]
         else:
-            raise ValueError(f"Unexpected file extension: {weights_path}, supported extensions are .pt, .pkl, and .pkl.gz")
-        if config_path is not None:
-            cfg = VisionModelSAERunnerConfig.load_config(config_path)
-        elif isinstance(payload, dict) and "cfg" in payload:
-            cfg = payload["cfg"]
-        else:
-            raise ValueError("No config found: pass config_path or use a checkpoint that embeds 'cfg'")
+            cfg_file = config_path or os.path.join(os.path.dirname(weights_path), "config.json")
+            if not os.path.isfile(cfg_file):
+                raise FileNotFoundError(f"No config file found at {cfg_file} and no legacy format detected")
+            loaded_cfg = VisionModelSAERunnerConfig.load_config(cfg_file)
+            weights = payload["state_dict"] if combined else payload
+        if not hasattr(loaded_cfg, "activation_fn_kwargs"):                # checkpoints older than the TopK option
+            loaded_cfg.activation_fn_kwargs = ({"negative_slope": 0.01} if getattr(loaded_cfg, "activation_fn_str", "relu") == "leaky_relu"
+                                               else {})
         if current_cfg is not None:
-            cfg._device, cfg._dtype = current_cfg._device, current_cfg._dtype
-        state = payload["state_dict"] if isinstance(payload, dict) and "state_dict" in payload else payload
-        instance = cls(cfg)
-        instance.load_state_dict(state)
+            items = current_cfg.items() if hasattr(current_cfg, "items") else vars(current_cfg).items()
+            for key, value in items:
+                if hasattr(loaded_cfg, key):
+                    try:
+                        setattr(loaded_cfg, key, value)
+                    except AttributeError:       # read-only derived property on the config
+                        pass
+        if getattr(loaded_cfg, "is_transcoder", False):
+            from vit_prisma.sae.transcoder import Transcoder
+            model_cls = Transcoder
+        elif loaded_cfg.architecture in ("standard", "vanilla"):
+            model_cls = StandardSparseAutoencoder
+        elif loaded_cfg.architecture == "gated":
+            model_cls = GatedSparseAutoencoder
+        else:
+            raise ValueError(f"Unsupported architecture type: {loaded_cfg.architecture}")
+        instance = model_cls(loaded_cfg)
+        instance.load_state_dict(weights)
         return instance
 
     def get_name(self) -> str:
@@ -239,7 +267,9 @@ class StandardSparseAutoencoder(SparseAutoencoder):
         dense = act == "relu" or bool(self.cfg.use_ghost_grads)
         wt, wd, be, bd = self._canonical_params()
         eng = self._engine
-        key = (wt.data_ptr(), wd.data_ptr(), be.data_ptr(), bd.data_ptr(), gemm_impl, dense)
+        if eng is not None and getattr(eng, "is_data_parallel", False) and eng._key[:4] == self._engine_key(gemm_impl, dense)[:4]:
+            return eng                       # the peer-memory engine owns the parameter storage: never rebuilt behind the trainer's back
+        key = self._engine_key(gemm_impl, dense)
         if eng is None or eng._key != key:
             k = self.cfg.activation_fn_kwargs["k"] if act == "topk" else 1
             kw = dict(k=k, normalize_activations=self._norm_mode, max_grad_norm=self.cfg.max_grad_norm, gemm_impl=gemm_impl)
@@ -253,6 +283,11 @@ class StandardSparseAutoencoder(SparseAutoencoder):
             self._engine = eng
         return eng
 
+    def _engine_key(self, gemm_impl: int, dense: bool):
+        """Identity of the storage a step engine is bound to (+ the options that change which engine class serves it)."""
+        wt, wd, be, bd = self._canonical_params()
+        return (wt.data_ptr(), wd.data_ptr(), be.data_ptr(), bd.data_ptr(), gemm_impl, dense)
+
     def enable_data_parallel(self, group, gemm_impl: int = L.GEMM_AUTO):
         """Move the parameters into NVLink peer-visible buffers and make ``step_engine()`` return the data-parallel engine
         (vit_prisma/b200/p2p.py): every rank then feeds its own token shard to ``train_step`` and all ranks hold identical
@@ -265,7 +300,7 @@ class StandardSparseAutoencoder(SparseAutoencoder):
                           max_grad_norm=self.cfg.max_grad_norm, gemm_impl=gemm_impl)
         # the nn.Parameters become views of the shared buffers, so state_dict()/save_model() see what the kernels update
         self.W_enc.data, self.W_dec.data, self.b_enc.data, self.b_dec.data = eng.W_encT.t(), eng.W_dec, eng.b_enc, eng.b_dec
-        eng._key = (eng.W_encT.data_ptr(), eng.W_dec.data_ptr(), eng.b_enc.data_ptr(), eng.b_dec.data_ptr(), gemm_impl)
+        eng._key = self._engine_key(gemm_impl, False)
         eng._enc_version = self.W_enc._version
         self._engine = eng
         return eng

@@ -126,11 +126,12 @@ class VisionSAETrainer:
         layers = cfg.hook_point_layer if isinstance(cfg.hook_point_layer, list) else [cfg.hook_point_layer]
         layer_id = layers.index(cfg.hook_point_layer) if not isinstance(cfg.hook_point_layer, list) else 0
         medians = {}
-        acts = self.activations_store.storage_buffer.detach()[:, layer_id, :]
         if cfg.b_dec_init_method == "geometric_median":
+            acts = self.activations_store.storage_buffer.detach()[:, layer_id, :]
             medians[layer_id] = compute_geometric_median(acts.float(), maxiter=200).median
             self.sparse_coder.initialize_b_dec_with_precalculated(medians[layer_id])
         elif cfg.b_dec_init_method == "mean":
+            acts = self.activations_store.storage_buffer.detach()[:, layer_id, :]
             self.sparse_coder.initialize_b_dec_with_mean(acts)
         self.sparse_coder.train()
         return medians
@@ -189,26 +190,35 @@ class VisionSAETrainer:
         else:
             scalars = engine.train_step(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores)
         n_frac_active_tokens += sae_in.shape[0]
-        mse_loss = scalars[3]
+        # the engine's scalars buffer is rewritten by the next step: hand out copies (device-side, no host sync)
+        mse_loss = scalars[3].clone()
         loss = mse_loss            # TopK: loss == mse (no L1 term, train_sae.py:617-626)
+        ghost_loss = aux_loss = None
         if gated:                                                    # loss = mse + l1 + aux reconstruction (sae.py:744)
             l1_loss = engine.aux[0] * (engine.l1_coefficient / sae_in.shape[0])
-            loss = loss + l1_loss + engine.aux[1] / float(sae_in.shape[0])
+            aux_loss = engine.aux[1] / float(sae_in.shape[0])
+            loss = loss + l1_loss + aux_loss
         elif hasattr(engine, "aux"):                                 # device-side: loss = mse + l1 + ghost (sae.py:628)
             ghost_loss = engine.aux[1] / float(sae_in.shape[0] * engine.d)
             if cfg.activation_fn_str != "topk":
                 l1_loss = engine.aux[0] * (engine.l1_coefficient / sae_in.shape[0])
                 loss = loss + l1_loss
             loss = loss + ghost_loss
-        l0 = scalars[4]
+        l0 = scalars[4].clone()
         if self.cfg.log_to_wandb and (n_training_steps + 1) % self.cfg.wandb_log_frequency == 0:
             vals = engine.scalars_dict()
-            self._log({"losses/mse_loss": vals["mse"], "losses/overall_loss": vals["mse"], "metrics/l0": vals["l0"],
+            metrics = {"losses/mse_loss": vals["mse"], "losses/overall_loss": float(loss), "metrics/l0": vals["l0"],
                        "metrics/grad_norm": vals["grad_norm"], "details/current_learning_rate": lr,
                        "details/n_training_tokens": n_training_tokens,
                        "metrics/mean_passes_since_fired": n_forward_passes_since_fired.mean().item(),
-                       "sparsity/dead_features": (n_forward_passes_since_fired > cfg.dead_feature_window).sum().item()},
-                      n_training_steps)
+                       "sparsity/dead_features": (n_forward_passes_since_fired > cfg.dead_feature_window).sum().item()}
+            if l1_loss is not None:
+                metrics["losses/l1_loss"] = float(l1_loss)
+            if ghost_loss is not None:
+                metrics["losses/ghost_grad_loss"] = float(ghost_loss)
+            if aux_loss is not None:
+                metrics["losses/aux_reconstruction_loss"] = float(aux_loss)
+            self._log(metrics, n_training_steps)
         scheduler.step()
         return loss, mse_loss, l1_loss, l0, act_freq_scores, n_forward_passes_since_fired, n_frac_active_tokens
 
@@ -247,20 +257,23 @@ class VisionSAETrainer:
         self.initialize_geometric_medians()
         self.enable_data_parallel_if_requested()
         n_steps, n_tokens = 0, 0
+        world = self.p2p_group.world if self.p2p_group is not None else 1
         progress_every = progress_every or max(self.cfg.wandb_log_frequency, 1)
         pbar = tqdm(total=self.cfg.total_training_tokens, desc="Training SAE", mininterval=20)
         while n_tokens < self.cfg.total_training_tokens:
             layer_acts = self.activations_store.next_batch()
+            if world > 1 and layer_acts.shape[0] != self.cfg.train_batch_size:
+                continue          # data parallel: every rank must bring the same row count to the peer barriers (short tail batches are dropped)
             loss, mse_loss, l1_loss, l0, act_freq_scores, since_fired, n_frac_active_tokens = self.train_step(
                 sparse_autoencoder=self.sparse_coder, optimizer=optimizer, scheduler=scheduler, layer_acts=layer_acts,
                 n_training_steps=n_steps, n_training_tokens=n_tokens, act_freq_scores=act_freq_scores,
                 n_forward_passes_since_fired=since_fired, n_frac_active_tokens=n_frac_active_tokens)
             n_steps += 1
-            n_tokens += self.cfg.train_batch_size
+            n_tokens += self.cfg.train_batch_size * world        # tokens of the GLOBAL step (each rank's store feeds its own shard)
             if self.checkpoint_thresholds and n_tokens > self.checkpoint_thresholds[0]:
                 self.checkpoint(self.sparse_coder, n_tokens, act_freq_scores, n_frac_active_tokens)
                 self.checkpoint_thresholds.pop(0)
-            pbar.update(self.cfg.train_batch_size)
+            pbar.update(self.cfg.train_batch_size * world)
             if n_steps % progress_every == 0:                       # one host read per N steps, not per step
                 pbar.set_description(f"Training SAE: Loss: {loss.item():.4f}, MSE Loss: {mse_loss.item():.4f}, L0: {l0.item():.4f}", refresh=False)
         if self.cfg.n_checkpoints:

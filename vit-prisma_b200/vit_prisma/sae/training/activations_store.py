@@ -217,27 +217,70 @@ class SyntheticActivationsStore:
 
 
 class CacheVisionActivationStore:
-    """Serve pre-computed activation shards from ``cfg.cached_activations_path`` (reference :21-152)."""
+    """Serve pre-computed activation shards from ``cfg.cached_activations_path`` with the reference's half-buffer mixing
+    (reference :21-152): ``storage_buffer`` holds half a buffer, every refill concatenates a fresh half-buffer read from disk,
+    shuffles, keeps one half and serves the other.  One deliberate difference: the reference restarts at ``0.pt`` on every
+    refill (its file cursor is a local variable, :54), so it re-serves the first ``buffer`` tokens forever; here the cursor
+    (file index + offset inside the file) persists, walking all shards round-robin."""
 
     def __init__(self, cfg: Any):
         self.cfg = cfg
-        self.next_cache_idx = 0
-        self.dataloader = self._next_loader()
+        if not cfg.use_cached_activations:
+            raise ValueError("CacheVisionActivationStore cannot be initialized with cfg.use_cached_activations = False ")
+        self._file_idx, self._file_off, self._file = 0, 0, None
+        half = cfg.n_batches_in_buffer // 2
+        self.storage_buffer = self.get_buffer(half)
+        self.dataloader = self.get_data_loader()
 
-    def _next_loader(self):
-        path = f"{self.cfg.cached_activations_path}/{self.next_cache_idx}.pt"
+    def _num_layers(self) -> int:
+        hp = self.cfg.hook_point_layer
+        return len(hp) if isinstance(hp, list) else 1
+
+    def _open(self, idx: int) -> torch.Tensor:
+        path = f"{self.cfg.cached_activations_path}/{idx}.pt"
         if not os.path.exists(path):
-            if self.next_cache_idx == 0:
+            if idx == 0:
                 raise FileNotFoundError(path)
-            self.next_cache_idx = 0
-            path = f"{self.cfg.cached_activations_path}/0.pt"
-        data = torch.load(path, map_location=self.cfg.device, weights_only=True).to(self.cfg.dtype)
-        self.next_cache_idx += 1
-        return _ShuffledServer(data, self.cfg.train_batch_size)
+            return None
+        return torch.load(path, map_location=self.cfg.device, weights_only=True)
+
+    def _load_cached_activations(self, total_size, context_size, num_layers, d_in) -> torch.Tensor:
+        want = total_size * context_size
+        parts, have, gained_since_wrap = [], 0, True
+        while have < want:
+            if self._file is None:
+                self._file = self._open(self._file_idx)
+                if self._file is None:                      # past the last shard: start over (a cache smaller than the buffer repeats)
+                    if not gained_since_wrap:
+                        break
+                    self._file_idx, self._file_off, gained_since_wrap = 0, 0, False
+                    continue
+            take = self._file[self._file_off: self._file_off + (want - have)]
+            parts.append(take.to(self.cfg.dtype))
+            have += take.shape[0]
+            gained_since_wrap = gained_since_wrap or take.shape[0] > 0
+            self._file_off += take.shape[0]
+            if self._file_off >= self._file.shape[0]:
+                self._file, self._file_idx, self._file_off = None, self._file_idx + 1, 0
+        if not parts:
+            return torch.zeros((0, num_layers, d_in), dtype=self.cfg.dtype, device=self.cfg.device)
+        return torch.cat(parts, dim=0)
+
+    def get_buffer(self, n_batches_in_buffer: int) -> torch.Tensor:
+        cfg = self.cfg
+        return self._load_cached_activations(cfg.store_batch_size * n_batches_in_buffer, cfg.context_size, self._num_layers(), cfg.d_in)
+
+    def get_data_loader(self) -> Iterator[Any]:
+        half = self.cfg.n_batches_in_buffer // 2
+        mixing = torch.cat([self.get_buffer(half), self.storage_buffer], dim=0)
+        mixing = mixing[torch.randperm(mixing.shape[0], device=mixing.device)]
+        keep = mixing.shape[0] // 2
+        self.storage_buffer = mixing[:keep]
+        return _ShuffledServer(mixing[keep:], self.cfg.train_batch_size)
 
     def next_batch(self) -> torch.Tensor:
         try:
             return next(self.dataloader)
         except StopIteration:
-            self.dataloader = self._next_loader()
+            self.dataloader = self.get_data_loader()
             return next(self.dataloader)
