@@ -212,7 +212,7 @@ typedef struct {
   float lr, beta1, beta2, adam_eps, max_grad_norm /* <= 0: no clipping */;
   /* inputs / parameters */
   const float* x;           /* [rows][d] raw activations */
-  float* W_encT; float* W_encT_lo; float* W_dec; float* b_enc; float* b_dec;
+  float* W_encT; float* W_encT_lo /* tf32 residual plane of the dense 3xTF32 encoder; may be NULL */; float* W_dec; float* b_enc; float* b_dec;
   /* per-step work buffers */
   float *sae_in, *mu, *sd, *xsum;            /* [rows][d], [rows], [rows], [d] (written by pb_sae_prep) */
   int32_t* idx; float* val;                  /* [rows][k] TopK support of hidden_pre (written by pb_sae_topk) */
@@ -233,6 +233,9 @@ typedef struct {
   /* scratch of pb_sae_backward for features selected by more than 64 tokens (their lists are split across warps):
    * work_bytes >= 8 + 4*F + 8*(rows*k/32 + F + 1)                                                                        */
   void* work; int64_t work_bytes;
+  /* [2] max_f ||W_encT[f,:]||_2 and max_f ||W_encT[f,:] - tf32_trunc(.)||_2 AFTER this step's update, for the fused encoder's error bound
+   * (pb_sae_encode_topk_fused); may be NULL                                                                               */
+  float* enc_norm_max;
 } PbSaeStep;
 
 /* sae_in = norm_in(x) - b_dec (+ tf32 residual, row mean / std, column sums of x) -- sae.py:78-87, 557-566 */
@@ -257,6 +260,37 @@ PB_API int pb_sae_mse(const float* x, const float* out, float* xsum_scratch, flo
                       pb_stream_t stream);
 /* W[f,:] /= ||W[f,:]|| (set_decoder_norm_to_unit_norm, sae.py:275-277); optional tf32 residual */
 PB_API int pb_unit_norm_rows(float* W, float* W_lo, int32_t F, int32_t d, pb_stream_t stream);
+
+/* ------------------------------------------------ fused encoder -> TopK (no dense hidden_pre in HBM)
+ * Replaces `hidden_pre = sae_in @ W_enc + b_enc` (sae/sae.py:568-574) + `torch.topk(hidden_pre, k)` (TopK.forward, :803-805) by
+ *   phase 1  one-pass TF32 tcgen05 GEMM whose epilogue keeps, per token and per 128-feature segment, the c_keep largest
+ *            values as packed keys (cand: int32 [rows][d_sae / 128][c_keep]);
+ *   phase 2  per token: the m_cand best keys (16 more per round, up to 128, while the proof below fails), EXACT fp32
+ *            re-evaluation of those pre-activations, exact top-k of them, and a completeness proof with the per-row bound
+ *            |tf32 product - exact| <= ||a - trunc(a)|| max_f||w_f|| + ||a|| max_f||w_f - trunc(w_f)||; rows that fail are listed;
+ *   phase 4  exact recomputation + selection for the listed rows (normally none).
+ * Same outputs and ordering rules as pb_sae_topk.  phases = 0 runs all three.                                             */
+typedef struct {
+  int32_t rows, d, F, k;
+  int32_t c_keep;               /* 4, 6 or 8 keys kept per (token, 128-feature segment)                                   */
+  int32_t m_cand;               /* candidates re-evaluated exactly per token in the first round: k <= m_cand <= 128       */
+  int32_t phases;               /* bit mask 1 | 2 | 4 (0 = all)                                                           */
+  float err_coef;               /* safety factor on the error bound; <= 0: default 1.05                                   */
+  const float* sae_in;          /* [rows][d]                                                                              */
+  const float* W_encT;          /* [F][d] feature-major encoder                                                           */
+  const float* b_enc;           /* [F]                                                                                    */
+  const float* enc_norm_max;    /* [2] max_f ||W_encT[f,:]||, max_f ||W_encT[f,:] - tf32_trunc(.)|| (pb_rownorm_max / pb_sae_adam) */
+  int32_t* cand; int64_t cand_bytes;
+  int32_t* idx; float* val;     /* [rows][k]                                                                              */
+  float* feat_count;            /* [F] += selections, may be NULL                                                         */
+  int32_t* fb_count;            /* [2]: rows that took the exact path in this call; candidates re-scored over the other rows */
+  int32_t* fb_rows;             /* [rows]                                                                                 */
+  float* fb_scratch; int64_t fb_scratch_bytes;   /* >= F * 4 bytes; one d_sae row per resident CTA of the exact path      */
+} PbSaeEncode;
+PB_API int pb_sae_fused_workspace(int32_t rows, int32_t F, int32_t c_keep, int64_t* cand_bytes, int64_t* fb_scratch_bytes);
+PB_API int pb_sae_encode_topk_fused(const PbSaeEncode* e, pb_stream_t stream);
+/* out[0] = max_f ||W[f,:]||_2, out[1] = max_f ||W[f,:] - tf32_trunc(W[f,:])||_2 over the rows of a contiguous fp32 [F][d] matrix */
+PB_API int pb_rownorm_max(const float* W, int32_t F, int32_t d, float* out, pb_stream_t stream);
 
 /* ------------------------------------------------ dense SAE step pieces (activation_fn_str = "relu" + L1) and ghost grads
  * StandardSparseAutoencoder.forward with a dense activation executes six [tokens x d_sae x d_in] products

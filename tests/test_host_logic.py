@@ -189,7 +189,7 @@ def test_c_abi_struct_layouts_match_the_compiled_library():
     from vit_prisma.b200 import p2p, sae_engine  # noqa: F401  (append PbSaeStep / PbP2PStep to ABI_STRUCTS)
     lib = ctypes.CDLL(str(L.LIB_PATH))
     lib.pb_abi_sizeof.restype = ctypes.c_int
-    assert len(L.ABI_STRUCTS) == 9
+    assert len(L.ABI_STRUCTS) == 10
     for idx, struct in enumerate(L.ABI_STRUCTS):
         if struct is None:      # device-side only struct
             assert lib.pb_abi_sizeof(idx) > 0

@@ -47,22 +47,99 @@ def test_topk_ties_and_negative_rows():
     assert dense[1].abs().sum().item() == 0 and dense[2, 7].item() == 5.0 and dense.shape == (3, 512)
 
 
+# ---------------------------------------------------------------------------- fused encoder -> TopK (csrc/sae_fused.cu)
+def _fused_case(rows, d, F, k, seed, scale_rows=None, w_scale=None, b_scale=0.01, **kw):
+    from vit_prisma.b200.sae_engine import SaeStepEngine
+    g = torch.Generator().manual_seed(seed)
+    W_encT = torch.randn(F, d, generator=g) / math.sqrt(d)
+    if w_scale is not None:
+        W_encT = W_encT * w_scale[:, None]
+    W_dec = torch.randn(F, d, generator=g)
+    W_dec /= W_dec.norm(dim=1, keepdim=True)
+    b_enc = b_scale * torch.randn(F, generator=g)
+    x = torch.randn(rows, d, generator=g) * 2.0 + torch.randn(d, generator=g)
+    if scale_rows is not None:
+        x = x * scale_rows[:, None]
+    eng = SaeStepEngine(W_encT.cuda(), W_dec.cuda(), b_enc.cuda(), torch.zeros(d).cuda(), k=k, normalize_activations="none", encoder="fused", **kw)
+    eng.encode_topk(x.cuda())
+    torch.cuda.synchronize()
+    hp = x.double() @ W_encT.double().t() + b_enc.double()                 # what sae.py:568 computes, in float64
+    return eng, hp
+
+
+def _check_against_float64(eng, hp, k):
+    ref = torch.topk(hp, k, dim=-1)
+    idx, val = eng.idx.cpu().long(), eng.val.cpu()
+    same = (idx == ref.indices).all(dim=1)
+    gap = torch.topk(hp, k + 1, dim=-1).values
+    srt = ref.values
+    # rows where two of the top k+1 float64 values are closer than fp32 round-off of the dot product may legitimately swap
+    near = ((srt[:, :-1] - srt[:, 1:]).abs().min(dim=1).values < 2e-6 * hp.abs().max()) | ((gap[:, k - 1] - gap[:, k]).abs() < 2e-6 * hp.abs().max())
+    assert bool((same | near).all()), f"{(~(same | near)).sum().item()} rows differ from the float64 top-k beyond near-ties"
+    assert same.float().mean().item() > 0.98
+    ok = same
+    assert rel_err(val[ok], ref.values[ok].float()) < 2e-6                 # re-scored values are fp32-exact, not tf32
+    assert bool((val[:, :-1] >= val[:, 1:]).all()), "values must come out sorted descending"
+    cnt = torch.zeros(hp.shape[1]).index_add_(0, idx.flatten(), torch.ones(idx.numel()))
+    assert torch.equal(eng.feat_count.cpu(), cnt)
+
+
+@pytest.mark.parametrize("rows,d,F,k,c_keep", [(300, 128, 2048, 8, 8), (257, 768, 24576, 32, 8), (129, 768, 24576, 32, 6), (64, 1024, 65536, 32, 4),
+                                               (130, 100, 1280, 16, 8)])
+def test_fused_encode_topk_matches_float64_topk(rows, d, F, k, c_keep):
+    eng, hp = _fused_case(rows, d, F, k, seed=rows + F, c_keep=c_keep)
+    _check_against_float64(eng, hp, k)
+    if F >= 2048:
+        assert eng.fallback_rows() <= max(2, rows // 50), f"{eng.fallback_rows()} of {rows} rows took the exact path on Gaussian data"
+
+
+def test_fused_encode_topk_adversarial_rows_take_the_exact_path():
+    """Cases the approximate pass cannot settle: constant rows (every value ties: lowest indices win), all winners inside one
+    128-feature segment (more than c_keep of them: saturation), and rows with a huge norm next to tiny ones (loose error bound)."""
+    from vit_prisma.b200.sae_engine import SaeStepEngine
+    d, F, k = 64, 1024, 16
+    W_encT = torch.zeros(F, d)
+    eng = SaeStepEngine(W_encT.cuda(), torch.eye(F, d).cuda().contiguous(), torch.zeros(F).cuda(), torch.zeros(d).cuda(), k=k,
+                        normalize_activations="none", encoder="fused")
+    eng.encode_topk(torch.randn(5, d).cuda())
+    assert eng.idx.cpu().tolist() == [list(range(k))] * 5 and eng.fallback_rows() == 5
+    # winners clustered in features 256..383: saturation of that segment
+    w_scale = torch.ones(F)
+    w_scale[256:384] = 50.0
+    eng2, hp2 = _fused_case(40, d, F, k, seed=3, w_scale=w_scale, b_scale=0.0)
+    hp2_abs = hp2                                                             # winners = largest of the boosted block (sign-dependent)
+    _check_against_float64(eng2, hp2_abs, k)
+    assert eng2.fallback_rows() >= 20
+    # mixed row norms: the bound scales per row
+    sr = torch.ones(64)
+    sr[::2] = 1e3
+    eng3, hp3 = _fused_case(64, 128, 4096, 8, seed=9, scale_rows=sr)
+    _check_against_float64(eng3, hp3, 8)
+
+
 # ---------------------------------------------------------------------------- engine vs reference goldens
-def _engine_from(p, k, norm, impl):
+def _engine_from(p, k, norm, impl, **kw):
     from vit_prisma.b200.sae_engine import SaeStepEngine
     W_encT = p["W_enc"].t().contiguous().cuda()
     return SaeStepEngine(W_encT, p["W_dec"].clone().cuda(), p["b_enc"].clone().cuda(), p["b_dec"].clone().cuda(), k=k,
-                         normalize_activations=norm, max_grad_norm=1.0, gemm_impl=impl)
+                         normalize_activations=norm, max_grad_norm=1.0, gemm_impl=impl, **kw)
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
-@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("impl", ["simt", "tc", "fused"])
 def test_train_steps_match_reference_golden(tag, impl):
-    """6 optimizer steps driven by the fused engine vs torch autograd + torch.optim.Adam on the reference module."""
+    """6 optimizer steps driven by the step engine vs torch autograd + torch.optim.Adam on the reference module.  ``fused`` is the
+    default encoder route (tf32 candidate GEMM + exact re-scoring): at d_sae = 256 / 512 every 128-feature segment is saturated, so
+    these runs also drive its exact path on every row."""
     L = _L()
     gold = load_golden(f"sae_tiny_{tag}.pt")
     data = _data(gold)
-    eng = _engine_from(gold["init"], gold["k"], gold["norm"], L.GEMM_SIMT if impl == "simt" else L.GEMM_TC)
+    if impl == "fused":
+        eng = _engine_from(gold["init"], gold["k"], gold["norm"], L.GEMM_AUTO)
+        assert eng.encoder == "fused"
+    else:
+        eng = _engine_from(gold["init"], gold["k"], gold["norm"], L.GEMM_SIMT if impl == "simt" else L.GEMM_TC)
+        assert eng.encoder == "dense"
     from vit_prisma.b200.sae_engine import unit_norm_rows_
     unit_norm_rows_(eng.W_dec)
     eng.refresh_lo()

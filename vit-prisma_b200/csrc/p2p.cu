@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
         st4(v_enc + base + 4 * c4, vv);
         for (int r = 0; r < t.world; ++r) {
           st4(t.W_encT[r] + base + 4 * c4, p);
-          st4(t.W_encT_lo[r] + base + 4 * c4, lo);
+          if (t.W_encT_lo[r]) st4(t.W_encT_lo[r] + base + 4 * c4, lo);     // tf32 residual plane: dense 3xTF32 encoder only
         }
       }
     }
@@ -353,4 +353,5 @@ extern "C" int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream) {
   return PB_OK;
 }
 
-int pb_abi_sizeof_p2p(int which) { return which == 8 ? (int)sizeof(PbP2PStep) : -1; }
+int pb_abi_sizeof_fused(int which);  // sae_fused.cu
+int pb_abi_sizeof_p2p(int which) { return which == 8 ? (int)sizeof(PbP2PStep) : pb_abi_sizeof_fused(which); }

@@ -659,10 +659,11 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
                                                        float* __restrict__ v_enc, float* __restrict__ m_be, float* __restrict__ v_be,
                                                        const float* __restrict__ fired, float* __restrict__ since_fired,
                                                        float* __restrict__ act_freq, const SaeScalars* __restrict__ sc, AdamHyper h,
-                                                       int F, int d, int renorm) {
+                                                       int F, int d, int renorm, float* __restrict__ enc_norm_max) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nvec = d >> 2;
   const float clip = sc->clip_coef;
+  float enc_best = 0.f, enc_best_lo = 0.f;
   for (int f = blockIdx.x * nw + warp; f < F; f += gridDim.x * nw) {
     const int64_t base = (int64_t)f * d;
     // ---- decoder row
@@ -712,6 +713,7 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
       }
     }
     // ---- encoder row (feature-major)
+    float esq = 0.f, elo = 0.f;
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
       const int c4 = i * 32 + lane;
@@ -725,6 +727,9 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
         for (int q = 0; q < 4; ++q) {
           p[q] = adam_update(p[q], gr[q] * clip, mm[q], vv[q], h);
           lo[q] = tf32_lo(p[q]);
+          esq = fmaf(p[q], p[q], esq);
+          const float tl = p[q] - tf32_trunc(p[q]);
+          elo = fmaf(tl, tl, elo);
         }
         st4(W_encT + base + 4 * c4, p);
         st4(m_enc + base + 4 * c4, mm);
@@ -732,6 +737,7 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
         if (W_encT_lo) st4(W_encT_lo + base + 4 * c4, lo);
       }
     }
+    if (enc_norm_max) { enc_best = fmaxf(enc_best, warp_sum(esq)); enc_best_lo = fmaxf(enc_best_lo, warp_sum(elo)); }
     if (lane == 0) {
       float mm = m_be[f], vv = v_be[f];
       b_enc[f] = adam_update(b_enc[f], gb_enc[f] * clip, mm, vv, h);
@@ -741,6 +747,12 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
       if (since_fired) since_fired[f] = fired[f] > 0.f ? 0.f : since_fired[f] + 1.f;
       if (act_freq) act_freq[f] += fired[f];
     }
+  }
+  // largest encoder-column norm after the update (error bound of the fused encoder's tf32 pass); norms are >= 0 so the
+  // bit pattern orders like the value
+  if (enc_norm_max && lane == 0 && enc_best > 0.f) {
+    atomicMax(reinterpret_cast<unsigned int*>(enc_norm_max), __float_as_uint(sqrtf(enc_best)));
+    atomicMax(reinterpret_cast<unsigned int*>(enc_norm_max) + 1, __float_as_uint(sqrtf(enc_best_lo)));
   }
 }
 
@@ -978,10 +990,11 @@ extern "C" int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream) {
   h.bc1 = 1.f - powf(s->beta1, (float)s->step);
   h.bc2_sqrt = sqrtf(1.f - powf(s->beta2, (float)s->step));
   const int grid = persistent_grid(8, F);
+  if (s->enc_norm_max) PB_CUDA(cudaMemsetAsync(s->enc_norm_max, 0, 2 * sizeof(float), st));
   PB_DISPATCH_CHUNKS(ch, (k_sae_adam_rows<C_><<<grid, 256, 0, st>>>(s->W_dec, s->W_encT, s->W_encT_lo, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc,
                                                                      s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, s->fired,
                                                                      s->since_fired, s->act_freq, (const SaeScalars*)s->scalars, h,
-                                                                     F, d, s->renorm_decoder)));
+                                                                     F, d, s->renorm_decoder, s->enc_norm_max)));
   PB_LAUNCH_CHECK();
   k_sae_adam_vec<<<(d + 255) / 256, 256, 0, st>>>(s->b_dec, s->gb_dec, s->m_bd, s->v_bd, (const SaeScalars*)s->scalars, h, d);
   PB_LAUNCH_CHECK();

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib as L
 from .ops import _stream
-from .sae_engine import PbSaeStep, SaeStepEngine
+from .sae_engine import PbSaeEncode, PbSaeStep, SaeStepEngine
 
 vp, i32, i64, f32, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32
 MAX_RANKS = 8
@@ -33,7 +33,7 @@ class PbP2PStep(C.Structure):
     )
 
 
-L.ABI_STRUCTS.extend([None, PbP2PStep])      # index 7 is the device-side scalars struct (no ctypes twin), 8 = PbP2PStep
+L.ABI_STRUCTS.extend([None, PbP2PStep, PbSaeEncode])   # 7 = device-side scalars struct (no ctypes twin), 8 = PbP2PStep, 9 = PbSaeEncode
 L.register_signatures({
     "pb_p2p_alloc": (i32, [i64, C.POINTER(vp), C.c_char_p]),
     "pb_p2p_open": (i32, [C.c_char_p, C.POINTER(vp)]),
@@ -112,6 +112,8 @@ class P2PGroup:
     def fill_tables(self, s: PbP2PStep) -> None:
         s.rank, s.world = self.rank, self.world
         for name in _TABLES:
+            if name not in self.peer_ptr:              # optional table (W_encT_lo): stays NULL
+                continue
             arr = getattr(s, name)
             for r, p in enumerate(self.peer_ptr[name]):
                 arr[r] = p
@@ -134,15 +136,15 @@ class SaeDPEngine(SaeStepEngine):
         shared["W_encT"].copy_(W_encT)
         shared["W_dec"].copy_(W_dec)
         shared["b_enc"].copy_(b_enc)
-        self._shared_lo = g.alloc("W_encT_lo", (F, d))
         for name, shape in (("gW_dec", (F, d)), ("gW_encT", (F, d)), ("gb_enc", (F,)), ("gb_dec", (d,)), ("fired", (F,)), ("xsum", (d,)),
                             ("norm_parts", (MAX_RANKS,))):
             g.alloc(name, shape)
         g.alloc("flags", (MAX_RANKS,), dtype=torch.int32)
         super().__init__(shared["W_encT"], shared["W_dec"], shared["b_enc"], b_dec.clone().contiguous(), k, **kw)
         # re-point the buffers peers must reach at the shared allocations
-        self.W_encT_lo = self._shared_lo
-        self.refresh_lo()
+        if self.W_encT_lo is not None:                 # dense 3xTF32 encoder: the residual plane is all-gathered with the parameters
+            self.W_encT_lo = g.alloc("W_encT_lo", (F, d))
+            self.refresh_lo()
         self.gW_dec, self.gW_encT, self.gb_enc, self.gb_dec = g.local["gW_dec"], g.local["gW_encT"], g.local["gb_enc"], g.local["gb_dec"]
         self.fired = g.local["fired"]
         self.xsum_local = g.local["xsum"]
@@ -192,6 +194,8 @@ class SaeDPEngine(SaeStepEngine):
         g.barrier(ps)                                   # norm partials published; all peer reads of this step are done
         L.check(lib.pb_p2p_adam_allgather(C.byref(ps), st), "pb_p2p_adam_allgather")
         g.barrier(ps)                                   # every rank holds the updated parameters
+        if self.encoder == "fused":                     # error bound of the next step's tf32 pass: largest encoder-column norm
+            L.check(lib.pb_rownorm_max(self.W_encT.data_ptr(), self.F, self.d, self.enc_norm_max.data_ptr(), st), "pb_rownorm_max")
         return self.scalars
 
     # ------------------------------------------------------------------ instrumentation: COLLECTIVE (every rank must call it)

@@ -133,6 +133,7 @@ class SaeDenseStepEngine(SaeStepEngine):
     """``SaeStepEngine`` plus the dense (ReLU + L1) step and the ghost-grad terms.  ``k`` is unused on the dense path."""
 
     def __init__(self, *a, l1_coefficient: float = 0.0, **kw):
+        kw["encoder"] = "dense"               # the dense / ghost terms read hidden_pre
         super().__init__(*a, **kw)
         self.l1_coefficient = float(l1_coefficient)
         self.aux = torch.zeros(4, device=self.W_dec.device)          # [l1_sum, ghost_sum, -, -]

@@ -34,7 +34,16 @@ class PbSaeStep(C.Structure):
             "csc_off", "csc_cursor", "csc_entries", "gW_dec", "gW_encT", "gb_enc", "gb_dec", "gcol", "gbdec2",
             "fired", "scalars", "m_dec", "v_dec", "m_enc", "v_enc", "m_be", "v_be", "m_bd", "v_bd",
             "since_fired", "act_freq")]
-        + [("global_rows", i32), ("dist", i32), ("work", vp), ("work_bytes", i64)]
+        + [("global_rows", i32), ("dist", i32), ("work", vp), ("work_bytes", i64), ("enc_norm_max", vp)]
+    )
+
+
+class PbSaeEncode(C.Structure):
+    """Fused encoder -> TopK call (include/prisma_b200.h, csrc/sae_fused.cu)."""
+    _fields_ = (
+        [(n, i32) for n in ("rows", "d", "F", "k", "c_keep", "m_cand", "phases")] + [("err_coef", f32)]
+        + [(n, vp) for n in ("sae_in", "W_encT", "b_enc", "enc_norm_max", "cand")] + [("cand_bytes", i64)]
+        + [(n, vp) for n in ("idx", "val", "feat_count", "fb_count", "fb_rows", "fb_scratch")] + [("fb_scratch_bytes", i64)]
     )
 
 
@@ -48,6 +57,9 @@ L.register_signatures({
     "pb_sae_adam": (i32, [C.POINTER(PbSaeStep), vp]),
     "pb_unit_norm_rows": (i32, [vp, vp, i32, i32, vp]),
     "pb_sae_mse": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+    "pb_sae_fused_workspace": (i32, [i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+    "pb_sae_encode_topk_fused": (i32, [C.POINTER(PbSaeEncode), vp]),
+    "pb_rownorm_max": (i32, [vp, i32, i32, vp, vp]),
 })
 
 NORM_MODE = {"none": 0, None: 0, "layer_norm": 1, "constant_norm_rescale": 2}
@@ -117,7 +129,7 @@ class SaeStepEngine:
 
     def __init__(self, W_encT: torch.Tensor, W_dec: torch.Tensor, b_enc: torch.Tensor, b_dec: torch.Tensor, k: int,
                  normalize_activations: str = "layer_norm", max_grad_norm: float = 1.0, betas=(0.9, 0.999), adam_eps: float = 1e-8,
-                 gemm_impl: int = L.GEMM_AUTO):
+                 gemm_impl: int = L.GEMM_AUTO, encoder: str = "auto", c_keep: int = 8, m_cand: Optional[int] = None):
         _need_cuda(W_encT, W_dec, b_enc, b_dec)
         for t in (W_encT, W_dec, b_enc, b_dec):
             if t.dtype != torch.float32 or not t.is_contiguous():
@@ -132,7 +144,20 @@ class SaeStepEngine:
         self.gemm_impl = gemm_impl
         dev = W_dec.device
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
-        self.W_encT_lo = torch.empty_like(W_encT)
+        # encoder route: "fused" = one-pass tf32 GEMM with a candidate epilogue + exact re-scoring (csrc/sae_fused.cu, no dense
+        # hidden_pre); "dense" = fp32-grade GEMM -> hidden_pre -> k_topk.  "auto" picks fused whenever the geometry allows it and
+        # the caller did not pin a GEMM implementation.
+        fused_ok = (self.d % 4 == 0 and self.d >= 32 and self.F % 128 == 0 and self.k <= 48 and (self.F // 128) * c_keep <= 8192)
+        if encoder == "auto":
+            encoder = "fused" if (fused_ok and gemm_impl == L.GEMM_AUTO) else "dense"
+        if encoder == "fused" and not fused_ok:
+            raise L.PrismaB200Error(f"fused encoder->TopK needs d_in % 4 == 0, d_sae % 128 == 0, k <= 48 (d={self.d} F={self.F} k={self.k})")
+        import os
+        self.encoder, self.c_keep = encoder, int(os.environ.get("PRISMA_SAE_C_KEEP", c_keep))     # env overrides: tuning runs only
+        self.m_cand = int(os.environ.get("PRISMA_SAE_M_CAND", 0)) or (int(m_cand) if m_cand else self.k + 8)   # first round; +16 per round while unproven
+        self.enc_norm_max = z(2)                      # max ||w_f||, max ||w_f - tf32_trunc(w_f)|| (error bound of the fused encoder)
+        self.fb_count = z(2, dt=torch.int32)          # rows on the exact path, candidates re-scored (last fused encode)
+        self.W_encT_lo = torch.empty_like(W_encT) if encoder == "dense" else None
         self.refresh_lo()
         # optimizer state (torch.optim.Adam: exp_avg / exp_avg_sq start at zero)
         self.m_dec, self.v_dec, self.m_enc, self.v_enc = z(self.F, self.d), z(self.F, self.d), z(self.F, self.d), z(self.F, self.d)
@@ -148,18 +173,29 @@ class SaeStepEngine:
         self._rows = -1
 
     def refresh_lo(self) -> None:
-        """Recompute the tf32 residual of the encoder (after an external write to the parameters)."""
-        from . import ops
-        self.W_encT_lo.copy_(ops.split_tf32(self.W_encT))
+        """Recompute what the encoder kernels derive from W_enc (after an external write to the parameters): the tf32 residual
+        plane of the dense 3xTF32 route, the largest encoder-column norm of the fused route's error bound."""
+        if self.W_encT_lo is not None:
+            from . import ops
+            self.W_encT_lo.copy_(ops.split_tf32(self.W_encT))
+        L.check(L.get_lib().pb_rownorm_max(self.W_encT.data_ptr(), self.F, self.d, self.enc_norm_max.data_ptr(), _stream()), "pb_rownorm_max")
 
     def _ensure_rows(self, rows: int) -> None:
         if rows == self._rows:
             return
         dev, d, F, k = self.W_dec.device, self.d, self.F, self.k
         e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
-        self.sae_in, self.sae_in_lo, self.g, self.sae_out = e(rows, d), e(rows, d), e(rows, d), e(rows, d)
+        self.sae_in, self.g, self.sae_out = e(rows, d), e(rows, d), e(rows, d)
         self.mu, self.sd = e(rows), e(rows)
-        self.hidden_pre = e(rows, F)
+        if self.encoder == "fused":
+            cb, sb = i64(0), i64(0)
+            L.check(L.get_lib().pb_sae_fused_workspace(rows, F, self.c_keep, C.byref(cb), C.byref(sb)), "pb_sae_fused_workspace")
+            self.cand = e(max(cb.value // 4, 4), dt=torch.int32)
+            self.fb_rows = e(max(rows, 1), dt=torch.int32)
+            self.fb_scratch = e(min(64, max(sb.value // (4 * F), 1)) * F)      # exact path: one d_sae row per resident CTA
+            self.sae_in_lo = self.hidden_pre = None
+        else:
+            self.sae_in_lo, self.hidden_pre = e(rows, d), e(rows, F)
         self.idx, self.val, self.dval = e(rows, k, dt=torch.int32), e(rows, k), e(rows, k)
         self.csc_entries = e(rows * k, dt=torch.int32)
         self.work = e(8 + 4 * F + 8 * (rows * k // 32 + F + 1) + 64, dt=torch.uint8)   # hot-feature work lists (pb_sae_backward)
@@ -185,7 +221,18 @@ class SaeStepEngine:
         s.m_be, s.v_be, s.m_bd, s.v_bd = p(self.m_be), p(self.v_be), p(self.m_bd), p(self.v_bd)
         s.since_fired, s.act_freq = p(since_fired), p(act_freq)
         s.work, s.work_bytes = p(self.work), self.work.numel()
+        s.enc_norm_max = p(self.enc_norm_max)
         return s
+
+    def _enc_desc(self, rows: int, phases: int = 0) -> PbSaeEncode:
+        e = PbSaeEncode()
+        e.rows, e.d, e.F, e.k, e.c_keep, e.m_cand, e.phases, e.err_coef = rows, self.d, self.F, self.k, self.c_keep, self.m_cand, phases, 0.0
+        e.sae_in, e.W_encT, e.b_enc, e.enc_norm_max = self.sae_in.data_ptr(), self.W_encT.data_ptr(), self.b_enc.data_ptr(), self.enc_norm_max.data_ptr()
+        e.cand, e.cand_bytes = self.cand.data_ptr(), self.cand.numel() * 4
+        e.idx, e.val, e.feat_count = self.idx.data_ptr(), self.val.data_ptr(), self.feat_count.data_ptr()
+        e.fb_count, e.fb_rows = self.fb_count.data_ptr(), self.fb_rows.data_ptr()
+        e.fb_scratch, e.fb_scratch_bytes = self.fb_scratch.data_ptr(), self.fb_scratch.numel() * 4
+        return e
 
     # ------------------------------------------------------------------ pieces
     def _encoder_gemm(self, rows: int) -> None:
@@ -205,12 +252,15 @@ class SaeStepEngine:
         lib, st = L.get_lib(), _stream()
         rows = x.shape[0]
         self._ensure_rows(rows)
-        use_tc = self.gemm_impl != L.GEMM_SIMT
         L.check(lib.pb_sae_prep(x.data_ptr(), self.b_dec.data_ptr(), self.sae_in.data_ptr(),
-                                self.sae_in_lo.data_ptr() if use_tc else None, self.mu.data_ptr(), self.sd.data_ptr(),
+                                self.sae_in_lo.data_ptr() if (self.sae_in_lo is not None and self.gemm_impl != L.GEMM_SIMT) else None,
+                                self.mu.data_ptr(), self.sd.data_ptr(),
                                 self.xsum.data_ptr(), rows, self.d, self.norm_mode, st), "pb_sae_prep")
-        self._encoder_gemm(rows)
         self.feat_count.zero_()
+        if self.encoder == "fused":
+            L.check(lib.pb_sae_encode_topk_fused(C.byref(self._enc_desc(rows)), st), "pb_sae_encode_topk_fused")
+            return
+        self._encoder_gemm(rows)
         scratch = self.topk_scratch
         L.check(lib.pb_sae_topk(self.hidden_pre.data_ptr(), rows, self.F, self.k, self.idx.data_ptr(), self.val.data_ptr(),
                                 self.feat_count.data_ptr(), None if scratch is None else scratch.data_ptr(),
@@ -245,7 +295,19 @@ class SaeStepEngine:
 
     # ------------------------------------------------------------------ instrumentation (bench.py / tools)
     def describe_encoder(self) -> str:
+        if self.encoder == "fused":
+            return (f"fused: one-pass tf32 tcgen05 GEMM with top-{self.c_keep}-per-128-features epilogue -> exact fp32 re-scoring of "
+                    f">= {self.m_cand} candidates per token -> exact top-{self.k} with a completeness proof (no dense hidden_pre)")
         return "tcgen05 3xTF32 GEMM -> dense hidden_pre -> exact k_topk" if self.gemm_impl != L.GEMM_SIMT else "exact FFMA GEMM -> k_topk"
+
+    def fallback_rows(self) -> int:
+        """Rows of the last fused encode that took the exact path (host read: synchronises)."""
+        return int(self.fb_count[0].item()) if self.encoder == "fused" else 0
+
+    def rescored_per_row(self, rows: int) -> float:
+        """Mean number of candidates re-scored exactly per proven row in the last fused encode (host read: synchronises)."""
+        fb, tot = self.fb_count.tolist()
+        return tot / max(rows - fb, 1)
 
     def _optimizer_stages(self, s: PbSaeStep, x: torch.Tensor, lr: float, since_fired, act_freq):
         """(name, callable, info) of the stages after backward; the data-parallel engine replaces them with its peer-memory phases."""
@@ -293,6 +355,18 @@ class SaeStepEngine:
 
     def _encode_stages(self, x: torch.Tensor):
         rows = x.shape[0]
+        if self.encoder == "fused":
+            lib, st = L.get_lib(), _stream()
+            self.encode_topk(x)
+            flops = 2.0 * rows * self.d * self.F
+            nkeys = (self.F // 128) * self.c_keep
+            return [("encode + topk, fused (prep + tf32 candidate GEMM + select / exact re-score + exact path)", lambda: self.encode_topk(x),
+                     dict(flops=flops, passes=1)),
+                    ("candidate GEMM alone (one tf32 pass, top-c-per-segment epilogue)",
+                     lambda: L.check(lib.pb_sae_encode_topk_fused(C.byref(self._enc_desc(rows, 1)), st)),
+                     dict(flops=flops, passes=1, bytes=4 * self.d * self.F + 4 * rows * self.d + 4 * rows * nkeys, ncu=r"k_enc_cand")),
+                    ("select + exact re-score alone", lambda: L.check(lib.pb_sae_encode_topk_fused(C.byref(self._enc_desc(rows, 2)), st)),
+                     dict(bytes=4 * rows * nkeys + 4 * rows * self.d + 8 * rows * self.k, ncu=r"k_cand_select"))]
         return [("encode + topk (prep + encoder GEMM 3xTF32 + exact topk)", lambda: self.encode_topk(x),
                  dict(flops=2.0 * rows * self.d * self.F, passes=3, ncu=r"k_gemm_tc2<float")),
                 ("encoder GEMM alone (hidden_pre = sae_in @ W_enc + b_enc)", lambda: self._encoder_gemm(rows),

@@ -43,6 +43,7 @@ class SaeGatedStepEngine(SaeStepEngine):
 
     def __init__(self, W_encT: torch.Tensor, W_dec: torch.Tensor, b_gate: torch.Tensor, r_mag: torch.Tensor, b_mag: torch.Tensor,
                  b_dec: torch.Tensor, l1_coefficient: float, **kw):
+        kw["encoder"] = "dense"
         super().__init__(W_encT, W_dec, b_gate, b_dec, k=1, **kw)     # b_gate rides in the b_enc slot of pb_sae_adam
         _need_cuda(r_mag, b_mag)
         self.b_gate, self.r_mag, self.b_mag = b_gate, r_mag, b_mag

@@ -362,7 +362,9 @@ class StandardSparseAutoencoder(SparseAutoencoder):
                 # use_error_term: sae_out + (x - sae_out).detach() == x -- the clean activation flows on, the SAE's hooks still fired
                 return x if getattr(self, "use_error_term", False) else sae_out
             feature_acts = eng.dense_feature_acts().view(*lead, self.d_sae)
-            hidden_pre2 = eng.hidden_pre
+            hidden_pre2 = eng.hidden_pre       # None on the fused encoder route (no dense pre-activations exist)
+            if hidden_pre2 is None and want_ghost:
+                hidden_pre2, _ = ops.gemm(eng.sae_in, self._canonical_params()[0], self._canonical_params()[2])
         else:
             _, feature_acts, _hidden_pre = self.encode(x32, return_hidden_pre=True)
             sae_out = self.decode(feature_acts)
