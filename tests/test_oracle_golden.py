@@ -141,3 +141,21 @@ def test_gated_sae_oracle_matches_reference_training(tag):
             for name in GATED_PARAMS:
                 assert_close(p[name], rec["params_after"][name], 5e-5, f"step {s} param {name}")
     assert torch.equal(since_fired, gold["since_fired"]) and torch.equal(act_freq, gold["act_freq"])
+
+
+def test_geometric_median_matches_reference_fixture():
+    """b_dec_init_method="geometric_median" (reference sae/training/geometric_median.py:23-85; train_sae.py:245-276): our Weiszfeld
+    iteration against medians computed by the unmodified reference (tests/golden/make_golden_median.py), with and without outliers."""
+    from vit_prisma.sae.training.geometric_median import compute_geometric_median
+    for case in load_golden("geometric_median.pt"):
+        g = torch.Generator().manual_seed(case["seed"])
+        n, d = case["n"], case["d"]
+        pts = torch.randn(n, d, generator=g) * 2.0 + torch.randn(d, generator=g)
+        if case["outliers"]:
+            pts[:case["outliers"]] += 25.0 * torch.randn(case["outliers"], d, generator=g)
+        out = compute_geometric_median(pts, maxiter=case["maxiter"])
+        assert out.termination == case["termination"]
+        err = (out.median - case["median"]).abs().max().item() / case["median"].abs().max().item()
+        assert err <= 1e-5, (case["seed"], err)
+        if case["outliers"]:
+            assert (case["median"] - case["mean"]).norm() > 0.1          # the fixture really distinguishes median from mean

@@ -14,6 +14,8 @@
 //        fused clip + decoder-parallel-gradient removal + Adam + decoder row renorm + dead-feature counters.
 // No host synchronisation anywhere: scalars (loss, norm, clip coefficient) live in a device struct.
 #include "common.cuh"
+#include <stdlib.h>
+#include "tc_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // device scalars of one step
@@ -326,28 +328,51 @@ __global__ void __launch_bounds__(256) k_sae_decode(const float* __restrict__ x,
 
 // ---------------------------------------------------------------------------------------------
 // 4. CSC build: feat_count (float, from k_topk) -> offsets (exclusive scan) ; fill entries
+// One CTA of 1024 threads.  Batches of 16 chunks of 1024 counts: the 16 coalesced loads of a batch are issued together (one memory
+// latency), then each chunk is block-scanned (warp shuffles + one shared array of warp totals) on top of the running total.
+// (The first version gave every thread a contiguous run of F / 1024 counts: 2 x 24 dependent uncoalesced loads = 35 us of latency.)
 __global__ void __launch_bounds__(1024) k_scan_counts(const float* __restrict__ cnt, int* __restrict__ off, int* __restrict__ cursor, int F) {
-  __shared__ int part[1024];
-  const int t = threadIdx.x;
-  const int per = (F + 1023) / 1024;
-  const int a = t * per, b = min(F, a + per);
-  int s = 0;
-  for (int i = a; i < b; ++i) s += (int)cnt[i];
-  part[t] = s;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    int v = t >= o ? part[t - o] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
+  __shared__ int wtot[32];
+  __shared__ int carry_s;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int carry = 0;
+  for (int base = 0; base < F; base += 16 * 1024) {
+    int v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int p = base + i * 1024 + t;
+      v[i] = p < F ? (int)cnt[p] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (base + i * 1024 >= F) break;
+      int x = v[i];                                  // inclusive scan inside the warp
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) wtot[warp] = x;
+      __syncthreads();
+      if (warp == 0) {
+        int w = wtot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, w, o);
+          if (lane >= o) w += y;
+        }
+        wtot[lane] = w;                              // inclusive totals of warps 0..lane
+        if (lane == 31) carry_s = w;
+      }
+      __syncthreads();
+      const int excl = carry + (warp ? wtot[warp - 1] : 0) + x - v[i];
+      const int p = base + i * 1024 + t;
+      if (p < F) { off[p] = excl; cursor[p] = excl; }
+      carry += carry_s;
+      __syncthreads();
+    }
   }
-  int run = t ? part[t - 1] : 0;
-  for (int i = a; i < b; ++i) {
-    off[i] = run;
-    cursor[i] = run;
-    run += (int)cnt[i];
-  }
-  if (t == 1023) off[F] = part[1023];
+  if (t == 0) off[F] = carry;
 }
 __global__ void __launch_bounds__(256) k_csc_fill(const int* __restrict__ idx, int* __restrict__ cursor, int* __restrict__ entries, int64_t n) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -383,6 +408,9 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
   for (int c = threadIdx.x; c < d; c += blockDim.x) sm_bd[c] = 0.f;
   __syncthreads();
   float nsq = 0.f;
+  float bd[CHUNKS][4];
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) bd[i][0] = bd[i][1] = bd[i][2] = bd[i][3] = 0.f;
   for (int f = blockIdx.x * nw + warp; f < F; f += gridDim.x * nw) {
     const int e0 = off[f], e1 = off[f + 1];
     const int len = e1 - e0;
@@ -498,7 +526,7 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
           float w[4];
           ld4(W_encT + (int64_t)f * d + 4 * c4, w);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) atomicAdd(&sm_bd[4 * c4 + q], gbe * w[q]);
+          for (int q = 0; q < 4; ++q) bd[i][q] = fmaf(gbe, w[q], bd[i][q]);
         }
       }
     }
@@ -506,6 +534,18 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
       gb_enc[f] = gbe;
       fired[f] = npos;
       nsq += gbe * gbe;
+    }
+  }
+  // the -b_dec path, sum_f gb_enc[f] W_encT[f]: per-lane register partials over this warp's features, one shared-memory
+  // reduction per CTA (the per-feature shared atomics of the first version cost 24 x 64 cycles of the LSU per feature -- the
+  // whole kernel ran at the ATOMS rate, profiles/r02_sae_notes.md)
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c4 = i * 32 + lane;
+    if (c4 < nvec) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (bd[i][q] != 0.f) atomicAdd(&sm_bd[4 * c4 + q], bd[i][q]);
     }
   }
   nsq = warp_sum(nsq);
@@ -536,6 +576,9 @@ __global__ void __launch_bounds__(256) k_sae_grads_long(const int* __restrict__ 
   if (n_items == 0) return;
   for (int c = threadIdx.x; c < d; c += blockDim.x) sm_bd[c] = 0.f;
   __syncthreads();
+  float bd[CHUNKS][4];
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) bd[i][0] = bd[i][1] = bd[i][2] = bd[i][3] = 0.f;
   for (int item = blockIdx.x * nw + warp; item < n_items; item += gridDim.x * nw) {
     const int f = work_chunks[2 * item], p0 = work_chunks[2 * item + 1];
     const int p1 = min(off[f + 1], p0 + SAE_LONG_CHUNK);
@@ -574,13 +617,22 @@ __global__ void __launch_bounds__(256) k_sae_grads_long(const int* __restrict__ 
           float w[4];
           ld4(W_encT + (int64_t)f * d + 4 * c4, w);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) atomicAdd(&sm_bd[4 * c4 + q], gbe * w[q]);
+          for (int q = 0; q < 4; ++q) bd[i][q] = fmaf(gbe, w[q], bd[i][q]);
         }
       }
     }
     if (lane == 0) {
       atomicAdd(gb_enc + f, gbe);
       atomicAdd(fired + f, npos);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c4 = i * 32 + lane;
+    if (c4 < nvec) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (bd[i][q] != 0.f) atomicAdd(&sm_bd[4 * c4 + q], bd[i][q]);
     }
   }
   __syncthreads();
@@ -754,6 +806,183 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
     atomicMax(reinterpret_cast<unsigned int*>(enc_norm_max), __float_as_uint(sqrtf(enc_best)));
     atomicMax(reinterpret_cast<unsigned int*>(enc_norm_max) + 1, __float_as_uint(sqrtf(enc_best_lo)));
   }
+}
+
+// ---- 7b. the same update as a bulk-copy pipeline ---------------------------------------------------------------------
+// k_sae_adam_rows keeps a feature's rows in registers: its loads are issued in four dependent waves per feature (w,g -> m,v ->
+// encoder row), 16 warps per SM, and it reaches 0.63 of the HBM copy bandwidth.  Here one producer lane streams every feature's
+// EIGHT rows (W_dec, gW_dec, m_dec, v_dec, W_encT, gW_encT, m_enc, v_enc: 8 x d x 4 bytes) into a shared-memory ring with
+// cp.async.bulk (completion on an mbarrier), AB_NW consumer warps update one feature each in place, and the six result rows go
+// back with cp.async.bulk stores.  The bytes in flight per SM are set by the ring depth (S x 24 KB at d = 768), not by registers.
+constexpr int AB_NW = 6;
+constexpr int AB_THREADS = 32 * (1 + AB_NW);
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+k_sae_adam_bulk(float* __restrict__ W_dec, float* __restrict__ W_encT, float* __restrict__ b_enc, const float* __restrict__ gW_dec,
+                const float* __restrict__ gW_encT, const float* __restrict__ gb_enc, float* __restrict__ m_dec, float* __restrict__ v_dec,
+                float* __restrict__ m_enc, float* __restrict__ v_enc, float* __restrict__ m_be, float* __restrict__ v_be,
+                const float* __restrict__ fired, float* __restrict__ since_fired, float* __restrict__ act_freq,
+                const SaeScalars* __restrict__ sc, AdamHyper h, int F, int d, int renorm, float* __restrict__ enc_norm_max, int S) {
+  extern __shared__ __align__(128) unsigned char ab_smem[];
+  const uint32_t s0 = smem_u32(ab_smem);
+  const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = 8u * row_bytes;
+  auto full_bar = [&](int s) { return s0 + 8u * s; };
+  auto empty_bar = [&](int s) { return s0 + 8u * (S + s); };
+  const uint32_t data0 = s0 + 256u;                       // barriers live in the first 256 bytes (S <= 16)
+  float* data_generic = reinterpret_cast<float*>(ab_smem + 256);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_mine = F > (int)blockIdx.x ? (F - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_mine; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (uint32_t)(i / S) & 1u;
+        const int64_t base = (int64_t)(blockIdx.x + (int64_t)i * gridDim.x) * d;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), stage_bytes);
+        const uint32_t dst = data0 + (uint32_t)s * stage_bytes;
+        bulk_load(dst + 0 * row_bytes, W_dec + base, row_bytes, full_bar(s));
+        bulk_load(dst + 1 * row_bytes, gW_dec + base, row_bytes, full_bar(s));
+        bulk_load(dst + 2 * row_bytes, m_dec + base, row_bytes, full_bar(s));
+        bulk_load(dst + 3 * row_bytes, v_dec + base, row_bytes, full_bar(s));
+        bulk_load(dst + 4 * row_bytes, W_encT + base, row_bytes, full_bar(s));
+        bulk_load(dst + 5 * row_bytes, gW_encT + base, row_bytes, full_bar(s));
+        bulk_load(dst + 6 * row_bytes, m_enc + base, row_bytes, full_bar(s));
+        bulk_load(dst + 7 * row_bytes, v_enc + base, row_bytes, full_bar(s));
+      }
+    }
+    return;
+  }
+  const int nvec = d >> 2;
+  const float clip = sc->clip_coef;
+  float enc_best = 0.f, enc_best_lo = 0.f;
+  for (int i = warp - 1; i < n_mine; i += AB_NW) {
+    const int s = i % S;
+    const uint32_t ph = (uint32_t)(i / S) & 1u;
+    const int f = blockIdx.x + i * gridDim.x;
+    const int64_t base = (int64_t)f * d;
+    // per-feature scalars: in flight while the rows arrive
+    float be = 0.f, gbe = 0.f, mbe = 0.f, vbe = 0.f, fr = 0.f, sf = 0.f, af = 0.f;
+    if (lane == 0) {
+      be = b_enc[f]; gbe = gb_enc[f]; mbe = m_be[f]; vbe = v_be[f]; fr = fired[f];
+      if (since_fired) sf = since_fired[f];
+      if (act_freq) af = act_freq[f];
+    }
+    mbar_wait(full_bar(s), ph);
+    float* st = data_generic + (size_t)s * 8 * d;
+    float *wd = st, *gd = st + d, *md = st + 2 * d, *vd = st + 3 * d, *we = st + 4 * d, *ge = st + 5 * d, *me = st + 6 * d, *ve = st + 7 * d;
+    // ---- decoder row: clip, remove the component parallel to the (unit-norm) row, Adam, renormalise
+    float w[CHUNKS][4], gq[CHUNKS][4];
+    float par = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int c4 = c * 32 + lane;
+      if (c4 < nvec) {
+        ld4(wd + 4 * c4, w[c]);
+        ld4(gd + 4 * c4, gq[c]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { gq[c][q] *= clip; par = fmaf(gq[c][q], w[c][q], par); }
+      } else {
+        w[c][0] = w[c][1] = w[c][2] = w[c][3] = gq[c][0] = gq[c][1] = gq[c][2] = gq[c][3] = 0.f;
+      }
+    }
+    par = warp_sum(par);
+    float nsq = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int c4 = c * 32 + lane;
+      if (c4 < nvec) {
+        float mm[4], vv[4];
+        ld4(md + 4 * c4, mm);
+        ld4(vd + 4 * c4, vv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float gr = gq[c][q] - par * w[c][q];
+          w[c][q] = adam_update(w[c][q], gr, mm[q], vv[q], h);
+          nsq += w[c][q] * w[c][q];
+        }
+        st4(md + 4 * c4, mm);
+        st4(vd + 4 * c4, vv);
+      }
+    }
+    const float nrm = sqrtf(warp_sum(nsq));
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int c4 = c * 32 + lane;
+      if (c4 < nvec) {
+        if (renorm) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[c][q] = w[c][q] / nrm;
+        }
+        st4(wd + 4 * c4, w[c]);
+      }
+    }
+    // ---- encoder row
+    float esq = 0.f, elo = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int c4 = c * 32 + lane;
+      if (c4 < nvec) {
+        float p[4], gr[4], mm[4], vv[4];
+        ld4(we + 4 * c4, p);
+        ld4(ge + 4 * c4, gr);
+        ld4(me + 4 * c4, mm);
+        ld4(ve + 4 * c4, vv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          p[q] = adam_update(p[q], gr[q] * clip, mm[q], vv[q], h);
+          esq = fmaf(p[q], p[q], esq);
+          const float tl = p[q] - tf32_trunc(p[q]);
+          elo = fmaf(tl, tl, elo);
+        }
+        st4(we + 4 * c4, p);
+        st4(me + 4 * c4, mm);
+        st4(ve + 4 * c4, vv);
+      }
+    }
+    enc_best = fmaxf(enc_best, warp_sum(esq));
+    enc_best_lo = fmaxf(enc_best_lo, warp_sum(elo));
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes above -> visible to the bulk-copy engine
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t src = data0 + (uint32_t)s * stage_bytes;
+      bulk_store(W_dec + base, src + 0 * row_bytes, row_bytes);
+      bulk_store(m_dec + base, src + 2 * row_bytes, row_bytes);
+      bulk_store(v_dec + base, src + 3 * row_bytes, row_bytes);
+      bulk_store(W_encT + base, src + 4 * row_bytes, row_bytes);
+      bulk_store(m_enc + base, src + 6 * row_bytes, row_bytes);
+      bulk_store(v_enc + base, src + 7 * row_bytes, row_bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // bias + dead-feature bookkeeping (train_sae.py:356-361) while the stores drain
+      b_enc[f] = adam_update(be, gbe * clip, mbe, vbe, h);
+      m_be[f] = mbe;
+      v_be[f] = vbe;
+      if (since_fired) since_fired[f] = fr > 0.f ? 0.f : sf + 1.f;
+      if (act_freq) act_freq[f] = af + fr;
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the ring slot has been read: hand it back
+      mbar_arrive(empty_bar(s));
+    }
+  }
+  if (enc_norm_max && lane == 0 && enc_best > 0.f) {
+    atomicMax(reinterpret_cast<unsigned int*>(enc_norm_max), __float_as_uint(sqrtf(enc_best)));
+    atomicMax(reinterpret_cast<unsigned int*>(enc_norm_max) + 1, __float_as_uint(sqrtf(enc_best_lo)));
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256) k_sae_adam_vec(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -991,6 +1220,40 @@ extern "C" int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream) {
   h.bc2_sqrt = sqrtf(1.f - powf(s->beta2, (float)s->step));
   const int grid = persistent_grid(8, F);
   if (s->enc_norm_max) PB_CUDA(cudaMemsetAsync(s->enc_norm_max, 0, 2 * sizeof(float), st));
+  static int bulk_mode = -1;        // PB_SAE_ADAM=rows forces the register kernel (A/B measurements)
+  if (bulk_mode < 0) { const char* e = getenv("PB_SAE_ADAM"); bulk_mode = (e && !strcmp(e, "rows")) ? 0 : 1; }
+  if (bulk_mode && !s->W_encT_lo && d % 4 == 0 && d >= 64) {      // no tf32 residual plane to maintain: the bulk-copy pipeline
+    const size_t stage = (size_t)8 * d * 4;
+    int S = (int)((200 * 1024) / stage);
+    if (S > 12) S = 12;
+    if (S >= 3) {
+      const size_t smem = 256 + (size_t)S * stage;
+      int g2 = pb_sm_count();
+      if (g2 > F) g2 = F;
+#define PB_ADAM_BULK(CH)                                                                                                              \
+  do {                                                                                                                                \
+    auto kern = k_sae_adam_bulk<CH>;                                                                                                  \
+    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                     \
+    kern<<<g2, AB_THREADS, smem, st>>>(s->W_dec, s->W_encT, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc, s->m_dec, s->v_dec, s->m_enc, \
+                                       s->v_enc, s->m_be, s->v_be, s->fired, s->since_fired, s->act_freq, (const SaeScalars*)s->scalars, \
+                                       h, F, d, s->renorm_decoder, s->enc_norm_max, S);                                              \
+  } while (0)
+      switch (ch) {
+        case 1: PB_ADAM_BULK(1); break;
+        case 2: PB_ADAM_BULK(2); break;
+        case 4: PB_ADAM_BULK(4); break;
+        case 6: PB_ADAM_BULK(6); break;
+        case 8: PB_ADAM_BULK(8); break;
+        case 12: PB_ADAM_BULK(12); break;
+        default: pb_set_error("sae: d_in=%d unsupported", d); return PB_EUNSUPPORTED;
+      }
+#undef PB_ADAM_BULK
+      PB_LAUNCH_CHECK();
+      k_sae_adam_vec<<<(d + 255) / 256, 256, 0, st>>>(s->b_dec, s->gb_dec, s->m_bd, s->v_bd, (const SaeScalars*)s->scalars, h, d);
+      PB_LAUNCH_CHECK();
+      return PB_OK;
+    }
+  }
   PB_DISPATCH_CHUNKS(ch, (k_sae_adam_rows<C_><<<grid, 256, 0, st>>>(s->W_dec, s->W_encT, s->W_encT_lo, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc,
                                                                      s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, s->fired,
                                                                      s->since_fired, s->act_freq, (const SaeScalars*)s->scalars, h,

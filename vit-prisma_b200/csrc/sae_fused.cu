@@ -223,8 +223,8 @@ constexpr int SEL_EXTEND = 16;      // candidates added per extension round
 //   2. rounds: exactly re-score the first m_cur candidates (m_cand, then +16 per round), take the exact top-k of those, and try
 //      to prove no other feature can beat the k-th:   ub(best key not yet re-scored) + E_row < tau_k.  Most rows are proven in
 //      the first round; a row that runs out of ranked candidates (or whose segment kept-lists are saturated) is listed.
-template <int IPT>
-__global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ cand, int nkeys, int c_keep, const float* __restrict__ sae_in,
+template <int SPT>
+__global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ cand, int nseg, int c_keep, const float* __restrict__ sae_in,
                                                      const float* __restrict__ W_encT, const float* __restrict__ b_enc,
                                                      const float* __restrict__ wnorm_max, float err_scale, int d, int k, int m_cand, int gcap,
                                                      int* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ feat_count,
@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int row = blockIdx.x;
   const int nvec = d >> 2;
+  const int nkeys = nseg * c_keep;
 
   // ---- the token's encoder input -> shared memory; ||a|| and ||a - tf32_trunc(a)|| for the error bound
   {
@@ -259,15 +260,24 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
     lsq = warp_sum(lsq);
     if (lane == 0) { red[0][warp] = nsq; red[1][warp] = lsq; }
   }
-  // ---- keys of this row: per-thread best
-  int key[IPT];
+  // ---- keys of this row.  Thread t owns WHOLE segments t, t + 256, ... (their c_keep keys, sorted descending by the GEMM
+  // epilogue), so a thread's best key is the largest segment maximum it holds and the thread bests are evenly spread.  (Striding
+  // single keys over the threads put every segment maximum into the threads with t % c_keep == 0 when c_keep divides 256: the
+  // threshold below fell to the 4th-best-of-segment level and 3x too many keys were gathered and ranked.)
+  int key[SPT][8];
   int bk = INT_MIN;
   const int* kr = cand + (int64_t)row * nkeys;
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int p = t + 256 * i;
-    key[i] = p < nkeys ? kr[p] : INT_MIN;
-    bk = max(bk, key[i]);
+  for (int i = 0; i < SPT; ++i) {
+    const int sg = t + 256 * i;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      int2 v = make_int2(INT_MIN, INT_MIN);
+      if (sg < nseg && j < c_keep) v = *reinterpret_cast<const int2*>(kr + sg * c_keep + j);
+      key[i][j] = v.x;
+      key[i][j + 1] = v.y;
+    }
+    bk = max(bk, key[i][0]);
   }
   best[t] = bk;
   if (t == 0) { g_n = 0; u_below = INT_MIN; tau_key = INT_MIN; sk_next = INT_MIN; }
@@ -278,7 +288,7 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
     a_norm = sqrtf(s0);
     a_lo_norm = sqrtf(s1);
   }
-  const int m_tau = min(min(SEL_MAX_CAND, 256), nkeys);
+  const int m_tau = min(min(SEL_MAX_CAND, 256), nseg);   // that many threads hold at least one segment
   {
     int rank = 0;
     for (int j = 0; j < 256; ++j) rank += (best[j] > bk || (best[j] == bk && j < t)) ? 1 : 0;
@@ -288,14 +298,19 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
   const int tau = tau_key;
   int lower = INT_MIN;                              // best key of this thread below tau
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int p = t + 256 * i;
-    if (p < nkeys) {
-      if (key[i] >= tau) {
-        const int slot = atomicAdd(&g_n, 1);
-        if (slot < gcap) { g_key[slot] = key[i]; g_pos[slot] = p; }
-      } else {
-        lower = max(lower, key[i]);
+  for (int i = 0; i < SPT; ++i) {
+    const int sg = t + 256 * i;
+    if (sg < nseg) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < c_keep) {
+          if (key[i][j] >= tau) {
+            const int slot = atomicAdd(&g_n, 1);
+            if (slot < gcap) { g_key[slot] = key[i][j]; g_pos[slot] = sg * c_keep + j; }
+          } else {
+            lower = max(lower, key[i][j]);
+          }
+        }
       }
     }
   }
@@ -350,9 +365,13 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
       const int key_m = sk[m_cur - 1];
       int sat = INT_MIN;
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) {
-        const int p = t + 256 * i;
-        if (p < nkeys && (p % c_keep) == c_keep - 1 && key[i] >= key_m) sat = max(sat, key[i]);
+      for (int i = 0; i < SPT; ++i) {
+        if (t + 256 * i < nseg) {
+          int last = key[i][3];                    // last kept key of the segment: slot c_keep - 1
+          if (c_keep == 6) last = key[i][5];
+          if (c_keep == 8) last = key[i][7];
+          if (last >= key_m) sat = max(sat, last);
+        }
       }
       if (sat != INT_MIN) atomicMax(&sat_key, sat);
     }
@@ -494,12 +513,13 @@ int launch_enc_cand(const PbSaeEncode* e, cudaStream_t st) {
   return PB_OK;
 }
 
-template <int IPT>
-int launch_select(const PbSaeEncode* e, int nkeys, float scale, cudaStream_t st) {
-  int gcap = IPT * SEL_MAX_CAND;       // keys >= threshold come from at most SEL_MAX_CAND threads (more only when bests tie: overflow -> exact path)
+template <int SPT>
+int launch_select(const PbSaeEncode* e, int nseg, float scale, cudaStream_t st) {
+  const int nkeys = nseg * e->c_keep;
+  int gcap = 8 * SEL_MAX_CAND;         // keys >= threshold: ~1.5 x SEL_MAX_CAND on typical rows; more only with heavy ties (overflow -> exact path)
   if (gcap > nkeys) gcap = nkeys;
   const size_t smem = sizeof(float) * e->d + 8 * (size_t)gcap;
-  k_cand_select<IPT><<<e->rows, 256, smem, st>>>(e->cand, nkeys, e->c_keep, e->sae_in, e->W_encT, e->b_enc, e->enc_norm_max, scale, e->d, e->k,
+  k_cand_select<SPT><<<e->rows, 256, smem, st>>>(e->cand, nseg, e->c_keep, e->sae_in, e->W_encT, e->b_enc, e->enc_norm_max, scale, e->d, e->k,
                                                   e->m_cand, gcap, e->idx, e->val, e->feat_count, e->fb_count, e->fb_rows, e->fb_count + 1);
   PB_LAUNCH_CHECK();
   return PB_OK;
@@ -526,7 +546,7 @@ extern "C" int pb_sae_encode_topk_fused(const PbSaeEncode* e, pb_stream_t stream
   PB_CHECK_ARG(pb_aligned16(e->sae_in) && pb_aligned16(e->W_encT) && pb_aligned16(e->b_enc) && pb_aligned16(e->cand),
                "pb_sae_encode_topk_fused: operands must be 16-byte aligned");
   const int nkeys = e->F / FZ_SEG * e->c_keep;
-  PB_CHECK_ARG(nkeys <= 256 * 32, "pb_sae_encode_topk_fused: d_sae=%d too large for the selection kernel", e->F);
+  PB_CHECK_ARG(e->F / FZ_SEG <= 256 * 4, "pb_sae_encode_topk_fused: d_sae=%d too large for the selection kernel (max 131072)", e->F);
   PB_CHECK_ARG(e->cand_bytes >= (int64_t)e->rows * nkeys * 4, "pb_sae_encode_topk_fused: candidate buffer too small");
   if (e->rows == 0) return PB_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -539,10 +559,10 @@ extern "C" int pb_sae_encode_topk_fused(const PbSaeEncode* e, pb_stream_t stream
   if (phases & 2) {
     PB_CUDA(cudaMemsetAsync(e->fb_count, 0, 2 * sizeof(int), st));    // [0] rows on the exact path, [1] candidates re-scored (proven rows)
     const float coef = e->err_coef > 0.f ? e->err_coef : 1.05f;       // safety factor on the Cauchy-Schwarz bound (norms evaluated in fp32)
-    const int ipt = (nkeys + 255) / 256;
-    if (ipt <= 8) PB_TRY(launch_select<8>(e, nkeys, coef, st));
-    else if (ipt <= 16) PB_TRY(launch_select<16>(e, nkeys, coef, st));
-    else PB_TRY(launch_select<32>(e, nkeys, coef, st));
+    const int nseg = e->F / FZ_SEG, spt = (nseg + 255) / 256;
+    if (spt <= 1) PB_TRY(launch_select<1>(e, nseg, coef, st));
+    else if (spt <= 2) PB_TRY(launch_select<2>(e, nseg, coef, st));
+    else PB_TRY(launch_select<4>(e, nseg, coef, st));
   }
   if (phases & 4) {
     PB_CHECK_ARG(e->fb_scratch && e->fb_scratch_bytes >= (int64_t)e->F * 4, "pb_sae_encode_topk_fused: fallback scratch missing");

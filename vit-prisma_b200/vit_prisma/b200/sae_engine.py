@@ -147,7 +147,7 @@ class SaeStepEngine:
         # encoder route: "fused" = one-pass tf32 GEMM with a candidate epilogue + exact re-scoring (csrc/sae_fused.cu, no dense
         # hidden_pre); "dense" = fp32-grade GEMM -> hidden_pre -> k_topk.  "auto" picks fused whenever the geometry allows it and
         # the caller did not pin a GEMM implementation.
-        fused_ok = (self.d % 4 == 0 and self.d >= 32 and self.F % 128 == 0 and self.k <= 48 and (self.F // 128) * c_keep <= 8192)
+        fused_ok = self.d % 4 == 0 and self.d >= 32 and self.F % 128 == 0 and self.k <= 48 and self.F <= 131072
         if encoder == "auto":
             encoder = "fused" if (fused_ok and gemm_impl == L.GEMM_AUTO) else "dense"
         if encoder == "fused" and not fused_ok:
