@@ -9,7 +9,8 @@ The default invocation (what the driver runs) measures BOTH hot paths and prints
   top level    the SAE training step (cfg #3: d_model 768, dict 768 x 32, TopK k = 32, 4096 tokens per step per GPU, fp32) driven
                through the public ``VisionSAETrainer.train_step`` -- the first half of BASELINE.json's metric and the only path with
                a collective (N > 1: NVLink peer-memory reduce-scatter + sharded Adam + all-gather, no NCCL on the data path);
-  "secondary"  the complete record of ``HookedViT.run_with_cache`` (cfg #2: CLIP ViT-B/32, batch 512 per GPU, all hook points).
+  "secondary"  the complete record of ``HookedViT.run_with_cache`` (cfg #2: CLIP ViT-B/32, batch 512 per GPU, all hook points) in
+               the reference's default dtype (fp32: 3xTF32 tensor-core products); "secondary_bf16" the same call with a bf16 model.
 
 Per record:
   value      whole-job throughput with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
@@ -356,7 +357,7 @@ def time_dominant_gemm(model, batch, dtype, iters=10):
     return {"ms": ms, "flops": 2.0 * M * N * K, "bytes": float(M * K * es + N * K * es + 2 * M * N * es), "shape": [M, N, K]}
 
 
-def run_vit(args, ctx):
+def run_vit(args, ctx, cpu_leg=True):
     from vit_prisma.b200 import _lib as L
     from vit_prisma.b200.synthetic import CLIP_B32, CLIP_L14
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
@@ -451,7 +452,7 @@ def run_vit(args, ctx):
             "step_algorithmic_tflops": flops_img * imgs / (dev_ms / 1e3) / 1e12,
             "step_mode_frac": flops_img * imgs / (dev_ms / 1e3) / 1e12 / (mode_peak if fp32 else (peaks["bf16_tflops_sustained"] or mode_peak)),
             "step_cache_write_gbs": cache_b_img * (1 if fp32 else 0.5) * imgs / (dev_ms / 1e3) / 1e9}
-    cpu = cpu_vit_images_per_sec(batch=4, cfg=CFG, layer=args.layer) if l14 else cpu_vit_images_per_sec()
+    cpu = None if not cpu_leg else (cpu_vit_images_per_sec(batch=4, cfg=CFG, layer=args.layer) if l14 else cpu_vit_images_per_sec())
     es = 4 if fp32 else 2
     rec = {"metric": vit_metric(l14, args.layer), "value": value, "unit": "images/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -632,7 +633,6 @@ def run_sae(args, ctx):
             "algorithmic_bytes": step_bytes, "peak_source": peaks["source"] + " HBM copy bandwidth",
             "dominant_kernel": dom, "stages": kernels}
     cpu = cpu_sae_tokens_per_sec()
-    nvlink_mb = int((world - 1) / world * (2 * d * F * 4 * 2 + d * F * 4) / 1e6)
     rec = {"metric": SAE_METRIC, "value": value, "unit": "tokens/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -640,8 +640,8 @@ def run_sae(args, ctx):
                       "tokens_per_step_per_gpu": Bt, "global_batch": Bt * world, "engine": type(eng).__name__,
                       "encoder": eng.describe_encoder(), "normalize_activations": "layer_norm", "max_grad_norm": 1.0,
                       "l2": "working set (2 x 75 MB weights + 2 x 150 MB Adam state + 150 MB gradients + 201 MB activation pool) larger than L2",
-                      "parallelism": f"dp{world}" + (" (NVLink peer-memory reduce-scatter + sharded Adam + all-gather, no NCCL on the data path; "
-                                                      f"{nvlink_mb} MB over NVLink per GPU per step)" if world > 1 else "")},
+                      "parallelism": f"dp{world}" + (" (reduce-scatter + sharded Adam + all-gather over NVLink, no NCCL on the data path; "
+                                                      + eng.describe_exchange() + ")" if world > 1 else "")},
            "clocks": clocks.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
            "final_loss": final_loss,
            "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * 4, "d2h_bytes_per_step": 4,
@@ -771,6 +771,12 @@ def main():
                 line = vit
             elif line is not None:
                 line["secondary"] = vit
+            if args.workload == "all" and args.dtype == "fp32":      # the throughput mode of the same path: bf16 operands, fp32 accumulation
+                vargs.dtype = "bf16"
+                vit16 = run_vit(vargs, ctx, cpu_leg=False)
+                if line is not None and vit16 is not None:
+                    vit16["cpu_baseline"] = vit["cpu_baseline"] if vit else None
+                    line["secondary_bf16"] = vit16
         if ctx.rank == 0 and line is not None:
             print(json.dumps(line), flush=True)
     finally:

@@ -370,6 +370,11 @@ typedef struct {
   float* b_dec; void* scalars;
   float *m_dec, *v_dec, *m_enc, *v_enc, *m_be, *v_be, *m_bd, *v_bd;   /* only the owned row slice is touched */
   float* since_fired; float* act_freq;
+  /* NVSwitch multicast views (pb_mc_*; all NULL = peer load / store path): the gradient matrices are then reduce-scattered with
+   * multimem.ld_reduce (summed in the switch) and the updated parameter rows all-gathered with multimem.st; the table entries
+   * [rank] above are this rank's own (unicast) mappings of the same memory, entries of other ranks are unused.             */
+  const float *mc_gW_dec, *mc_gW_encT;
+  float *mc_W_dec, *mc_W_encT, *mc_b_enc;
 } PbP2PStep;
 PB_API int pb_p2p_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* cudaMalloc (zeroed) + 64-byte IPC handle */
 PB_API int pb_p2p_open(const unsigned char* handle64, void** peer_ptr);
@@ -379,6 +384,15 @@ PB_API int pb_p2p_barrier(const PbP2PStep* s, uint32_t epoch, pb_stream_t stream
 PB_API int pb_p2p_sum_xsum(const PbP2PStep* s, float* xsum_global, pb_stream_t stream);
 PB_API int pb_p2p_reduce_scatter(const PbP2PStep* s, pb_stream_t stream);
 PB_API int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream);
+/* NVSwitch multicast memory (csrc/mc.cu).  Collective protocol, driven from the host side (vit_prisma/b200/p2p.py):
+ *   every rank pb_mc_supported -> rank 0 pb_mc_create (fd) -> fd to the other ranks (SCM_RIGHTS) -> pb_mc_import ->
+ *   every rank pb_mc_add_device -> barrier -> every rank pb_mc_bind_alloc -> barrier.  PB_EUNSUPPORTED = fall back.      */
+PB_API int pb_mc_supported(int32_t* supported);
+PB_API int pb_mc_round_size(int32_t world, int64_t bytes, int64_t* rounded);
+PB_API int pb_mc_create(int32_t world, int64_t bytes, uint64_t* mc_handle, int32_t* fd);
+PB_API int pb_mc_import(int32_t fd, uint64_t* mc_handle);
+PB_API int pb_mc_add_device(uint64_t mc_handle);
+PB_API int pb_mc_bind_alloc(uint64_t mc_handle, int64_t bytes, void** uc_ptr, void** mc_ptr, uint64_t* mem_handle);
 
 #ifdef __cplusplus
 }

@@ -119,5 +119,5 @@ def test_activations_store_with_a_real_model_matches_oracle_and_mixes_halves():
     served = torch.cat([store.next_batch() for _ in range(3)]).cpu()
     assert served.shape[1:] == (1, 128)
     rows = torch.cat([served[:, 0], store.storage_buffer[:64, 0].cpu()])
-    dist = torch.cdist(rows, bank).min(dim=1).values
-    assert float(dist.max()) <= 1e-3 * float(bank.abs().max()), float(dist.max())
+    dist = (rows[:, None, :].double() - bank[None, :, :].double()).abs().amax(dim=2).min(dim=1).values     # exact, no cdist cancellation
+    assert float(dist.max()) <= 1e-4 * float(bank.abs().max()), float(dist.max())

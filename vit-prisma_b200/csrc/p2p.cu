@@ -21,6 +21,22 @@
 
 #define PB_MAX_RANKS 8
 
+// NVSwitch multicast (mc.cu): one instruction reads the SUM of every rank's copy / writes every rank's copy
+__device__ __forceinline__ float4 mc_ld_reduce4(const float* mc_addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st4(float* mc_addr, const float (&v)[4]) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void mc_st1(float* mc_addr, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
+
 struct P2PTables {
   int rank, world;
   float* gW_dec[PB_MAX_RANKS];
@@ -102,18 +118,25 @@ __global__ void k_p2p_sum_small(P2PTables t, float* __restrict__ out, int which,
 // ------------------------------------------------------------------------------------------- reduce-scatter + norm
 // rows [f0, f1) of both gradient matrices: own += sum of peers; partial ||g||^2 -> every peer's norm_parts[rank]
 __global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PTables t, int f0, int f1, int d, const float* __restrict__ gb_enc_red,
-                                                           const float* __restrict__ gb_dec_red, int F, float* __restrict__ part_accum) {
+                                                           const float* __restrict__ gb_dec_red, int F, float* __restrict__ part_accum,
+                                                           const float* __restrict__ mc_gW_dec, const float* __restrict__ mc_gW_encT) {
   const int64_t n4 = (int64_t)(f1 - f0) * d / 4;
   const int64_t base4 = (int64_t)f0 * d / 4;
   float nsq = 0.f;
   for (int m = 0; m < 2; ++m) {
     float4* own = reinterpret_cast<float4*>(m == 0 ? t.gW_dec[t.rank] : t.gW_encT[t.rank]) + base4;
+    const float* mc = m == 0 ? mc_gW_dec : mc_gW_encT;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-      float4 acc = own[i];
-      for (int r = 0; r < t.world; ++r) {
-        if (r == t.rank) continue;
-        const float4 v = (reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4)[i];   // peer load (NVLink)
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      float4 acc;
+      if (mc) {
+        acc = mc_ld_reduce4(mc + 4 * (base4 + i));          // summed inside the switch: this slice crosses NVLink once
+      } else {
+        acc = own[i];
+        for (int r = 0; r < t.world; ++r) {
+          if (r == t.rank) continue;
+          const float4 v = (reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4)[i];   // peer load (NVLink)
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
       }
       own[i] = acc;
       nsq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
@@ -155,17 +178,22 @@ __global__ void k_p2p_finalize(P2PTables t, SaeScalarsP2P* sc, float max_norm, f
 
 // ------------------------------------------------------------------------------------------- Adam on owned rows + all-gather
 struct AdamHyperP2P { float lr, beta1, beta2, eps, bc1, bc2_sqrt; };
-__device__ __forceinline__ float adam_upd(float p, float gr, float& m, float& v, const AdamHyperP2P& h) {
+__device__ __forceinline__ float adam_upd(float p, float gr, float& m, float& v, const AdamHyperP2P& h) {   // same arithmetic as sae.cu adam_update
   m = h.beta1 * m + (1.f - h.beta1) * gr;
   v = h.beta2 * v + (1.f - h.beta2) * gr * gr;
-  return p - (h.lr / h.bc1) * (m / (sqrtf(v) / h.bc2_sqrt + h.eps));
+  float sq, rc;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+  const float denom = fmaf(sq, __frcp_rn(h.bc2_sqrt), h.eps);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(denom));
+  return fmaf(-(h.lr * __frcp_rn(h.bc1)) * m, rc, p);
 }
 
 template <int CHUNKS>
 __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0, int f1, int d, const float* __restrict__ gb_enc_red,
                                                            float* __restrict__ m_dec, float* __restrict__ v_dec, float* __restrict__ m_enc,
                                                            float* __restrict__ v_enc, float* __restrict__ m_be, float* __restrict__ v_be,
-                                                           const SaeScalarsP2P* __restrict__ sc, AdamHyperP2P h) {
+                                                           const SaeScalarsP2P* __restrict__ sc, AdamHyperP2P h, float* __restrict__ mc_W_dec,
+                                                           float* __restrict__ mc_W_encT, float* __restrict__ mc_b_enc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nvec = d >> 2;
   const float clip = sc->clip_coef;
@@ -207,14 +235,15 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
         st4(v_dec + base + 4 * c4, vv);
       }
     }
-    const float nrm = sqrtf(warp_sum(nsq));
+    const float inv_nrm = 1.f / sqrtf(warp_sum(nsq));
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
       const int c4 = i * 32 + lane;
       if (c4 < nvec) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[i][q] = w[i][q] / nrm;
-        for (int r = 0; r < t.world; ++r) st4(t.W_dec[r] + base + 4 * c4, w[i]);          // all-gather: peer stores
+        for (int q = 0; q < 4; ++q) w[i][q] = w[i][q] * inv_nrm;
+        if (mc_W_dec) mc_st4(mc_W_dec + base + 4 * c4, w[i]);                              // all-gather: one multicast store
+        else for (int r = 0; r < t.world; ++r) st4(t.W_dec[r] + base + 4 * c4, w[i]);      // all-gather: peer stores
       }
     }
 #pragma unroll
@@ -233,9 +262,13 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
         }
         st4(m_enc + base + 4 * c4, mm);
         st4(v_enc + base + 4 * c4, vv);
-        for (int r = 0; r < t.world; ++r) {
-          st4(t.W_encT[r] + base + 4 * c4, p);
-          if (t.W_encT_lo[r]) st4(t.W_encT_lo[r] + base + 4 * c4, lo);     // tf32 residual plane: dense 3xTF32 encoder only
+        if (mc_W_encT) {
+          mc_st4(mc_W_encT + base + 4 * c4, p);
+        } else {
+          for (int r = 0; r < t.world; ++r) {
+            st4(t.W_encT[r] + base + 4 * c4, p);
+            if (t.W_encT_lo[r]) st4(t.W_encT_lo[r] + base + 4 * c4, lo);     // tf32 residual plane: dense 3xTF32 encoder only
+          }
         }
       }
     }
@@ -244,7 +277,8 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
       const float nb = adam_upd(t.b_enc[t.rank][f], gb_enc_red[f] * clip, mm, vv, h);
       m_be[f] = mm;
       v_be[f] = vv;
-      for (int r = 0; r < t.world; ++r) t.b_enc[r][f] = nb;
+      if (mc_b_enc) mc_st1(mc_b_enc + f, nb);
+      else for (int r = 0; r < t.world; ++r) t.b_enc[r][f] = nb;
     }
   }
 }
@@ -311,7 +345,9 @@ extern "C" int pb_p2p_reduce_scatter(const PbP2PStep* s, pb_stream_t stream) {
   k_p2p_sum_small<<<(s->F + 255) / 256, 256, 0, st>>>(t, s->fired_red, 3, s->F);
   PB_LAUNCH_CHECK();
   PB_CUDA(cudaMemsetAsync(s->part_accum, 0, sizeof(float), st));
-  k_p2p_reduce_scatter<<<pb_sm_count() * 4, 256, 0, st>>>(t, f0, f1, s->d, s->gb_enc_red, s->gb_dec_red, s->F, s->part_accum);
+  PB_CHECK_ARG(!s->mc_gW_dec == !s->mc_gW_encT, "pb_p2p_reduce_scatter: both multicast gradient views or none");
+  k_p2p_reduce_scatter<<<pb_sm_count() * 4, 256, 0, st>>>(t, f0, f1, s->d, s->gb_enc_red, s->gb_dec_red, s->F, s->part_accum, s->mc_gW_dec,
+                                                          s->mc_gW_encT);
   PB_LAUNCH_CHECK();
   k_p2p_publish_norm<<<1, 32, 0, st>>>(t, s->part_accum);
   PB_LAUNCH_CHECK();
@@ -336,7 +372,8 @@ extern "C" int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream) {
   const int d = s->d;
   int grid = pb_sm_count() * 4;
   if (grid > (per + 7) / 8) grid = (per + 7) / 8;
-#define PB_P2P_ADAM(CH) k_p2p_adam_allgather<CH><<<grid, 256, 0, st>>>(t, f0, f1, d, s->gb_enc_red, s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, (const SaeScalarsP2P*)s->scalars, h)
+  PB_CHECK_ARG((!s->mc_W_dec == !s->mc_W_encT) && (!s->mc_W_dec == !s->mc_b_enc), "pb_p2p_adam_allgather: all three multicast parameter views or none");
+#define PB_P2P_ADAM(CH) k_p2p_adam_allgather<CH><<<grid, 256, 0, st>>>(t, f0, f1, d, s->gb_enc_red, s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, (const SaeScalarsP2P*)s->scalars, h, s->mc_W_dec, s->mc_W_encT, s->mc_b_enc)
   const int nvec = d / 4;
   if (d % 4 != 0 || nvec > 384) { pb_set_error("pb_p2p_adam_allgather: d_in=%d unsupported", d); return PB_EUNSUPPORTED; }
   if (nvec <= 32) PB_P2P_ADAM(1);

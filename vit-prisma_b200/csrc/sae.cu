@@ -393,7 +393,8 @@ __global__ void __launch_bounds__(256) k_csc_fill(const int* __restrict__ idx, i
 // 1e-7 level; the list is therefore sorted by token index first (lists are short: mean Bt*k/F).
 constexpr int SAE_LONG_LIST = 64;    // lists longer than this are split across warps
 constexpr int SAE_LONG_CHUNK = 32;   // entries per work item of the long-list kernel
-struct SaeWorkHeader { int n_chunks, n_long; };   // followed in memory by work_feats[F] and work_chunks[2 * capacity]
+struct SaeWorkHeader { int n_chunks, n_long, next_f, pad; };   // followed in memory by work_feats[F] and work_chunks[2 * capacity]
+constexpr int SAE_CLAIM = 4;         // features a warp claims per trip to the dynamic queue
 
 template <int CHUNKS>
 __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, int* __restrict__ entries, const float* __restrict__ val,
@@ -411,7 +412,14 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
   float bd[CHUNKS][4];
 #pragma unroll
   for (int i = 0; i < CHUNKS; ++i) bd[i][0] = bd[i][1] = bd[i][2] = bd[i][3] = 0.f;
-  for (int f = blockIdx.x * nw + warp; f < F; f += gridDim.x * nw) {
+  // dynamic queue: list lengths vary (mean Bt*k/F, long tail), and with a static feature -> warp map the CTA waited at its final
+  // barrier for its slowest warp (9.9 barrier-stall cycles per issue, profiles/r02_sae_step_ncu_summary.txt)
+  for (;;) {
+    int fbase = 0;
+    if (lane == 0) fbase = atomicAdd(&work->next_f, SAE_CLAIM);
+    fbase = __shfl_sync(0xffffffffu, fbase, 0);
+    if (fbase >= F) break;
+   for (int f = fbase; f < min(F, fbase + SAE_CLAIM); ++f) {
     const int e0 = off[f], e1 = off[f + 1];
     const int len = e1 - e0;
     if (len > SAE_LONG_LIST) {
@@ -535,6 +543,7 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
       fired[f] = npos;
       nsq += gbe * gbe;
     }
+   }
   }
   // the -b_dec path, sum_f gb_enc[f] W_encT[f]: per-lane register partials over this warp's features, one shared-memory
   // reduction per CTA (the per-feature shared atomics of the first version cost 24 x 64 cycles of the LSU per feature -- the
@@ -696,11 +705,18 @@ __global__ void __launch_bounds__(256) k_sae_finalize(const float* __restrict__ 
 //    and backward of every later step see identical numbers.
 struct AdamHyper { float lr, beta1, beta2, eps, bc1, bc2_sqrt; };  // bc1 = 1-beta1^t, bc2_sqrt = sqrt(1-beta2^t)
 
+// torch.optim.Adam (single tensor, no amsgrad / weight decay): m, v exactly as torch computes them; the parameter update
+// -(lr / bc1) m / (sqrt(v) / bc2_sqrt + eps) uses MUFU sqrt / reciprocal approximations (relative error ~1e-7 of an update that is
+// itself ~lr relative to the parameter: 1e-10 on the parameter, against a 1e-4 parity bar).  The IEEE sqrt + two divisions of the
+// first version were ~30 of the ~45 instructions per element and made the optimizer issue-bound (profiles/r02_sae_notes.md).
 __device__ __forceinline__ float adam_update(float p, float gr, float& m, float& v, const AdamHyper& h) {
   m = h.beta1 * m + (1.f - h.beta1) * gr;
   v = h.beta2 * v + (1.f - h.beta2) * gr * gr;
-  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
-  return p - (h.lr / h.bc1) * (m / denom);
+  float sq, rc;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+  const float denom = fmaf(sq, __frcp_rn(h.bc2_sqrt), h.eps);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(denom));
+  return fmaf(-(h.lr * __frcp_rn(h.bc1)) * m, rc, p);
 }
 
 template <int CHUNKS>
@@ -752,14 +768,14 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
         st4(v_dec + base + 4 * c4, vv);
       }
     }
-    const float nrm = sqrtf(warp_sum(nsq));
+    const float inv_nrm = 1.f / sqrtf(warp_sum(nsq));
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
       const int c4 = i * 32 + lane;
       if (c4 < nvec) {
         if (renorm) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) w[i][q] = w[i][q] / nrm;
+          for (int q = 0; q < 4; ++q) w[i][q] = w[i][q] * inv_nrm;
         }
         st4(W_dec + base + 4 * c4, w[i]);
       }
@@ -814,7 +830,7 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
 // EIGHT rows (W_dec, gW_dec, m_dec, v_dec, W_encT, gW_encT, m_enc, v_enc: 8 x d x 4 bytes) into a shared-memory ring with
 // cp.async.bulk (completion on an mbarrier), AB_NW consumer warps update one feature each in place, and the six result rows go
 // back with cp.async.bulk stores.  The bytes in flight per SM are set by the ring depth (S x 24 KB at d = 768), not by registers.
-constexpr int AB_NW = 6;
+constexpr int AB_NW = 12;
 constexpr int AB_THREADS = 32 * (1 + AB_NW);
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -919,14 +935,14 @@ k_sae_adam_bulk(float* __restrict__ W_dec, float* __restrict__ W_encT, float* __
         st4(vd + 4 * c4, vv);
       }
     }
-    const float nrm = sqrtf(warp_sum(nsq));
+    const float inv_nrm = 1.f / sqrtf(warp_sum(nsq));
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       const int c4 = c * 32 + lane;
       if (c4 < nvec) {
         if (renorm) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) w[c][q] = w[c][q] / nrm;
+          for (int q = 0; q < 4; ++q) w[c][q] = w[c][q] * inv_nrm;
         }
         st4(wd + 4 * c4, w[c]);
       }

@@ -216,28 +216,37 @@ __device__ __forceinline__ void warp_dot2(const float4* __restrict__ a4, const f
 
 constexpr int SEL_MAX_CAND = 128;   // most candidates one row may re-score before it gives up and takes the exact path
 constexpr int SEL_EXTEND = 16;      // candidates added per extension round
+constexpr int SEL_TAU_RANK = 96;    // the gather threshold keeps at least this many keys (typically 1.2-1.5x as many)
+constexpr int SEL_SLOTS = 512;      // gathered keys that can be sorted; more (massive ties) -> exact path
 
-// One CTA (256 threads) per token row.  dynamic smem: a_row[d] | g_key[gcap] | g_pos[gcap]
-//   1. gather the row's keys that can matter: all keys >= the SEL_MAX_CAND-th best per-thread best (>= SEL_MAX_CAND keys), rank
-//      them by counting -> the best SEL_MAX_CAND keys in order (sk / sp);
-//   2. rounds: exactly re-score the first m_cur candidates (m_cand, then +16 per round), take the exact top-k of those, and try
-//      to prove no other feature can beat the k-th:   ub(best key not yet re-scored) + E_row < tau_k.  Most rows are proven in
-//      the first round; a row that runs out of ranked candidates (or whose segment kept-lists are saturated) is listed.
+__device__ __forceinline__ unsigned long long sel_pack(int key, int pos) {    // orders like (key descending-first, pos ascending-first)
+  return ((unsigned long long)((unsigned)key ^ 0x80000000u) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)pos);
+}
+__device__ __forceinline__ int sel_key(unsigned long long it) { return (int)((unsigned)(it >> 32) ^ 0x80000000u); }
+__device__ __forceinline__ int sel_pos(unsigned long long it) { return (int)(0xFFFFFFFFu - (unsigned)it); }
+
+// One CTA (256 threads) per token row.  dynamic smem: a_row[d]
+//   1. threshold: every warp bitonic-sorts its 32 per-thread bests (= segment maxima) in registers and reports its q-th largest;
+//      the smallest report is a key with at least SEL_TAU_RANK keys of the row at or above it;
+//   2. gather the keys >= threshold (packed with their position) and bitonic-sort them in shared memory (256 or 512 slots);
+//   3. rounds: exactly re-score the first m_cur sorted candidates (m_cand, then +16 per round), take the exact top-k of those,
+//      and try to prove no other feature can beat the k-th:   ub(best key not yet re-scored) + E_row < tau_k.  Most rows are
+//      proven in the first round; a row that runs out of sorted candidates (or whose segment kept-lists saturate) is listed.
+// (The first version ranked by counting -- 256^2 + G^2 shared-memory compares per row -- and was ALU-bound at 205 us per launch,
+//  75 % issue-active, with the re-scoring gathers a small part of it: profiles/r02_sae_notes.md.)
 template <int SPT>
 __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ cand, int nseg, int c_keep, const float* __restrict__ sae_in,
                                                      const float* __restrict__ W_encT, const float* __restrict__ b_enc,
-                                                     const float* __restrict__ wnorm_max, float err_scale, int d, int k, int m_cand, int gcap,
+                                                     const float* __restrict__ wnorm_max, float err_scale, int d, int k, int m_cand,
                                                      int* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ feat_count,
                                                      int* __restrict__ fb_count, int* __restrict__ fb_rows, int* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   float* a_row = reinterpret_cast<float*>(sm_raw);
-  int* g_key = reinterpret_cast<int*>(a_row + d);
-  int* g_pos = g_key + gcap;
-  __shared__ int best[256];
-  __shared__ int sk[SEL_MAX_CAND], sp[SEL_MAX_CAND], ex_idx[SEL_MAX_CAND];
+  __shared__ unsigned long long items[SEL_SLOTS];
+  __shared__ int ex_idx[SEL_MAX_CAND], win_idx[64], warp_tau[8];
   __shared__ float ex_val[SEL_MAX_CAND];
   __shared__ float red[2][8];
-  __shared__ int tau_key, g_n, u_below, sk_next, sat_key, win_idx[64];
+  __shared__ int g_n, u_below, sat_key;
   __shared__ float tau_exact, a_norm, a_lo_norm;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int row = blockIdx.x;
@@ -261,9 +270,7 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
     if (lane == 0) { red[0][warp] = nsq; red[1][warp] = lsq; }
   }
   // ---- keys of this row.  Thread t owns WHOLE segments t, t + 256, ... (their c_keep keys, sorted descending by the GEMM
-  // epilogue), so a thread's best key is the largest segment maximum it holds and the thread bests are evenly spread.  (Striding
-  // single keys over the threads put every segment maximum into the threads with t % c_keep == 0 when c_keep divides 256: the
-  // threshold below fell to the 4th-best-of-segment level and 3x too many keys were gathered and ranked.)
+  // epilogue), so a thread's best key is the largest segment maximum it holds.
   int key[SPT][8];
   int bk = INT_MIN;
   const int* kr = cand + (int64_t)row * nkeys;
@@ -279,8 +286,27 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
     }
     bk = max(bk, key[i][0]);
   }
-  best[t] = bk;
-  if (t == 0) { g_n = 0; u_below = INT_MIN; tau_key = INT_MIN; sk_next = INT_MIN; }
+  // ---- threshold.  Warp w holds cnt_w = clamp(nthr - 32 w, 0, 32) valid bests (nthr = threads that own a segment); its quota
+  // q_w = ceil(m_tau cnt_w / nthr) of them are >= its q_w-th largest, and the quotas add up to >= m_tau.
+  {
+    int v = bk;                                     // bitonic sort across the warp, descending: lane i ends with the i-th largest
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        const int o = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool keep_max = ((lane & kk) == 0) == ((lane & j) == 0);
+        v = keep_max ? max(v, o) : min(v, o);
+      }
+    }
+    const int nthr = min(256, nseg);
+    const int m_tau = min(SEL_TAU_RANK, nthr);
+    const int cnt_w = max(0, min(32, nthr - 32 * warp));
+    const int q_w = (m_tau * cnt_w + nthr - 1) / nthr;
+    const int rep = __shfl_sync(0xffffffffu, v, max(q_w - 1, 0));
+    if (lane == 0) warp_tau[warp] = q_w > 0 ? rep : INT_MAX;
+  }
+  if (t == 0) { g_n = 0; u_below = INT_MIN; }
   __syncthreads();
   if (t == 0) {
     float s0 = 0.f, s1 = 0.f;
@@ -288,14 +314,10 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
     a_norm = sqrtf(s0);
     a_lo_norm = sqrtf(s1);
   }
-  const int m_tau = min(min(SEL_MAX_CAND, 256), nseg);   // that many threads hold at least one segment
-  {
-    int rank = 0;
-    for (int j = 0; j < 256; ++j) rank += (best[j] > bk || (best[j] == bk && j < t)) ? 1 : 0;
-    if (rank == m_tau - 1) tau_key = bk;            // at least m_tau keys of the row are >= tau_key
-  }
-  __syncthreads();
-  const int tau = tau_key;
+  int tau = INT_MAX;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tau = min(tau, warp_tau[w]);
+  // ---- gather
   int lower = INT_MIN;                              // best key of this thread below tau
 #pragma unroll
   for (int i = 0; i < SPT; ++i) {
@@ -306,7 +328,7 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
         if (j < c_keep) {
           if (key[i][j] >= tau) {
             const int slot = atomicAdd(&g_n, 1);
-            if (slot < gcap) { g_key[slot] = key[i][j]; g_pos[slot] = sg * c_keep + j; }
+            if (slot < SEL_SLOTS) items[slot] = sel_pack(key[i][j], sg * c_keep + j);
           } else {
             lower = max(lower, key[i][j]);
           }
@@ -316,27 +338,37 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
   }
   if (lower != INT_MIN) atomicMax(&u_below, lower);
   __syncthreads();
-  const bool overflow = g_n > gcap;                 // only with massive ties (e.g. constant rows): such rows take the exact path
-  const int G = min(g_n, gcap);
-  for (int c = t; c < G; c += 256) {
-    const int kc = g_key[c], pc = g_pos[c];
-    int rank = 0;
-    for (int j = 0; j < G; ++j) rank += (g_key[j] > kc || (g_key[j] == kc && g_pos[j] < pc)) ? 1 : 0;
-    if (rank < SEL_MAX_CAND) { sk[rank] = kc; sp[rank] = pc; }
-    else if (rank == SEL_MAX_CAND) sk_next = kc;    // best gathered key beyond the ranked list
+  const bool overflow = g_n > SEL_SLOTS;            // only with massive ties (e.g. constant rows): such rows take the exact path
+  const int G = min(g_n, SEL_SLOTS);
+  const int n_sort = G <= 256 ? 256 : SEL_SLOTS;
+  for (int i = G + t; i < n_sort; i += 256) items[i] = 0ull;     // padding sorts last
+  __syncthreads();
+  // ---- bitonic sort of items[0, n_sort), descending
+  for (int kk = 2; kk <= n_sort; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int p = t; p < (n_sort >> 1); p += 256) {
+        const int i = 2 * j * (p / j) + (p % j);
+        const int o = i + j;
+        const unsigned long long x = items[i], y = items[o];
+        const bool desc = (i & kk) == 0;
+        if ((x < y) == desc) { items[i] = y; items[o] = x; }
+      }
+      __syncthreads();
+    }
   }
   const int Gs = min(G, SEL_MAX_CAND);
   const float4* a4 = reinterpret_cast<const float4*>(a_row);
   int m_prev = 0, m_cur = min(m_cand, Gs);
   bool ok = false;
   for (;;) {
-    __syncthreads();                                // sk / sp complete (first round); previous round's reads of the shared scalars done
     if (t == 0) sat_key = INT_MIN;
     // ---- exact re-evaluation of candidates [m_prev, m_cur): hidden_pre[f] = <sae_in, W_enc[:, f]> + b_enc[f]   (sae.py:568-574)
     for (int c = m_prev + 2 * warp; c < m_cur; c += 16) {
-      const int f0 = (sp[c] / c_keep) * FZ_SEG + (sk[c] & 127);
+      const unsigned long long it0 = items[c];
+      const int f0 = (sel_pos(it0) / c_keep) * FZ_SEG + (sel_key(it0) & 127);
       if (c + 1 < m_cur) {
-        const int f1 = (sp[c + 1] / c_keep) * FZ_SEG + (sk[c + 1] & 127);
+        const unsigned long long it1 = items[c + 1];
+        const int f1 = (sel_pos(it1) / c_keep) * FZ_SEG + (sel_key(it1) & 127);
         float v0, v1;
         warp_dot2(a4, reinterpret_cast<const float4*>(W_encT + (int64_t)f0 * d), reinterpret_cast<const float4*>(W_encT + (int64_t)f1 * d), nvec,
                   lane, v0, v1);
@@ -362,7 +394,7 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
     }
     // a segment whose c_keep kept keys were ALL re-scored may have dropped a value as large as its last kept key
     if (m_cur > 0) {
-      const int key_m = sk[m_cur - 1];
+      const int key_m = sel_key(items[m_cur - 1]);
       int sat = INT_MIN;
 #pragma unroll
       for (int i = 0; i < SPT; ++i) {
@@ -378,7 +410,7 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
     __syncthreads();
     // ---- proof of completeness for this round
     {
-      const int u_rest = m_cur < Gs ? sk[m_cur] : (G > SEL_MAX_CAND ? sk_next : u_below);   // best key not re-scored
+      const int u_rest = m_cur < G ? sel_key(items[m_cur]) : u_below;                      // best key not re-scored
       const int u = max(u_rest, sat_key);
       const float u_val = u == INT_MIN ? -INFINITY : ord2f((u & ~127) | 127);               // upper end of the key's value bucket
       // |tf32 product - exact| = |a_lo.w + a_hi.w_lo| <= ||a_lo|| max||w|| + ||a|| max||w_lo||   (Cauchy-Schwarz, per row)
@@ -386,6 +418,7 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
       ok = !overflow && m_cur >= k && (u_val + E < tau_exact);
     }
     if (ok || m_cur >= Gs) break;
+    __syncthreads();                                // everybody has read sat_key / tau_exact of this round
     m_prev = m_cur;
     m_cur = min(m_cur + SEL_EXTEND, Gs);
   }
@@ -515,12 +548,9 @@ int launch_enc_cand(const PbSaeEncode* e, cudaStream_t st) {
 
 template <int SPT>
 int launch_select(const PbSaeEncode* e, int nseg, float scale, cudaStream_t st) {
-  const int nkeys = nseg * e->c_keep;
-  int gcap = 8 * SEL_MAX_CAND;         // keys >= threshold: ~1.5 x SEL_MAX_CAND on typical rows; more only with heavy ties (overflow -> exact path)
-  if (gcap > nkeys) gcap = nkeys;
-  const size_t smem = sizeof(float) * e->d + 8 * (size_t)gcap;
+  const size_t smem = sizeof(float) * e->d;
   k_cand_select<SPT><<<e->rows, 256, smem, st>>>(e->cand, nseg, e->c_keep, e->sae_in, e->W_encT, e->b_enc, e->enc_norm_max, scale, e->d, e->k,
-                                                  e->m_cand, gcap, e->idx, e->val, e->feat_count, e->fb_count, e->fb_rows, e->fb_count + 1);
+                                                  e->m_cand, e->idx, e->val, e->feat_count, e->fb_count, e->fb_rows, e->fb_count + 1);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -18,7 +18,7 @@ from . import _lib as L
 from .ops import _stream
 from .sae_engine import PbSaeEncode, PbSaeStep, SaeStepEngine
 
-vp, i32, i64, f32, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32
+vp, i32, i64, f32, u32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32, C.c_uint64
 MAX_RANKS = 8
 _TABLES = ("gW_dec", "gW_encT", "gb_enc", "gb_dec", "fired", "xsum", "W_dec", "W_encT", "W_encT_lo", "b_enc", "norm_parts", "flags")
 
@@ -30,6 +30,7 @@ class PbP2PStep(C.Structure):
         + [(n, vp * MAX_RANKS) for n in _TABLES]
         + [(n, vp) for n in ("gb_enc_red", "gb_dec_red", "fired_red", "part_accum", "b_dec", "scalars",
                              "m_dec", "v_dec", "m_enc", "v_enc", "m_be", "v_be", "m_bd", "v_bd", "since_fired", "act_freq")]
+        + [(n, vp) for n in ("mc_gW_dec", "mc_gW_encT", "mc_W_dec", "mc_W_encT", "mc_b_enc")]     # NVSwitch multicast views (or NULL)
     )
 
 
@@ -43,6 +44,12 @@ L.register_signatures({
     "pb_p2p_sum_xsum": (i32, [C.POINTER(PbP2PStep), vp, vp]),
     "pb_p2p_reduce_scatter": (i32, [C.POINTER(PbP2PStep), vp]),
     "pb_p2p_adam_allgather": (i32, [C.POINTER(PbP2PStep), vp]),
+    "pb_mc_supported": (i32, [C.POINTER(i32)]),
+    "pb_mc_round_size": (i32, [i32, i64, C.POINTER(i64)]),
+    "pb_mc_create": (i32, [i32, i64, C.POINTER(u64), C.POINTER(i32)]),
+    "pb_mc_import": (i32, [i32, C.POINTER(u64)]),
+    "pb_mc_add_device": (i32, [u64]),
+    "pb_mc_bind_alloc": (i32, [u64, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
 })
 
 
@@ -95,6 +102,81 @@ class P2PGroup:
         self.local[name], self._ptr[name], self._handle[name] = t, ptr.value, handle.raw
         return t
 
+    # ------------------------------------------------------------------ NVSwitch multicast pool (csrc/mc.cu)
+    def try_multicast_pool(self, nbytes: int):
+        """COLLECTIVE.  One multicast object + one bound physical allocation per rank, ``nbytes`` (rounded up) each.  Returns
+        ``(own_ptr, multicast_ptr, rounded_bytes)`` or ``None`` when the fabric / driver does not support it or any rank failed
+        (every rank then takes the peer load / store path).  The multicast handle travels as a POSIX file descriptor over a
+        Unix-domain socket (SCM_RIGHTS); torch.distributed only carries the socket path and the go / no-go votes."""
+        import os
+        import socket
+        import tempfile
+        import torch.distributed as dist
+        lib = L.get_lib()
+        if os.environ.get("PRISMA_P2P_MULTICAST", "1") == "0" or not (dist.is_available() and dist.is_initialized()):
+            return None
+
+        def all_ok(flag: bool) -> bool:
+            t = torch.tensor([1 if flag else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item())
+
+        sup = i32(0)
+        lib.pb_mc_supported(C.byref(sup))
+        if not all_ok(bool(sup.value)):
+            self.multicast_note = "multicast not supported on this device / fabric"
+            return None
+        rounded = i64(0)
+        ok = lib.pb_mc_round_size(self.world, int(nbytes), C.byref(rounded)) == L.PB_OK
+        if not all_ok(ok):
+            self.multicast_note = "multicast granularity query failed: " + L.last_error()
+            return None
+        handle, fd, sock_path, srv = u64(0), i32(-1), [None], None
+        if self.rank == 0:
+            ok = lib.pb_mc_create(self.world, rounded.value, C.byref(handle), C.byref(fd)) == L.PB_OK
+            if ok:
+                sock_path[0] = os.path.join(tempfile.gettempdir(), f"prisma_mc_{os.getpid()}_{id(self) & 0xffff:x}.sock")
+                srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                if os.path.exists(sock_path[0]):
+                    os.unlink(sock_path[0])
+                srv.bind(sock_path[0])
+                srv.listen(self.world)
+        if not all_ok(ok):
+            self.multicast_note = "cuMulticastCreate failed: " + L.last_error()
+            return None
+        dist.broadcast_object_list(sock_path, src=0)
+        try:
+            if self.rank == 0:
+                for _ in range(self.world - 1):
+                    conn, _addr = srv.accept()
+                    socket.send_fds(conn, [b"mc"], [fd.value])
+                    conn.close()
+                srv.close()
+                os.unlink(sock_path[0])
+            else:
+                cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                cli.connect(sock_path[0])
+                _msg, fds, _flags, _addr = socket.recv_fds(cli, 16, 1)
+                cli.close()
+                ok = len(fds) == 1 and lib.pb_mc_import(fds[0], C.byref(handle)) == L.PB_OK
+        except OSError as e:       # noqa: PERF203
+            ok = False
+            self.multicast_note = f"fd exchange failed: {e}"
+        if not all_ok(ok):
+            self.multicast_note = getattr(self, "multicast_note", "") or ("multicast import failed: " + L.last_error())
+            return None
+        ok = lib.pb_mc_add_device(handle.value) == L.PB_OK
+        if not all_ok(ok):                       # doubles as the barrier "every device joined" that must precede the binds
+            self.multicast_note = "cuMulticastAddDevice failed: " + L.last_error()
+            return None
+        own, mc, mem = vp(), vp(), u64(0)
+        ok = lib.pb_mc_bind_alloc(handle.value, rounded.value, C.byref(own), C.byref(mc), C.byref(mem)) == L.PB_OK
+        if not all_ok(ok):                       # barrier: every rank has bound before anybody touches the multicast view
+            self.multicast_note = "multicast bind / map failed: " + L.last_error()
+            return None
+        self.multicast_note = f"NVSwitch multicast pool, {rounded.value >> 20} MiB per rank"
+        return own.value, mc.value, rounded.value
+
     def connect(self) -> None:
         """Swap IPC handles and open every peer's buffers (collective: call on all ranks after all ``alloc`` calls)."""
         everyone = self._exchange(dict(self._handle))
@@ -132,12 +214,35 @@ class SaeDPEngine(SaeStepEngine):
         F, d = W_dec.shape
         shard_bounds(F, group.rank, group.world)
         g = group
-        shared = {"W_encT": g.alloc("W_encT", (F, d)), "W_dec": g.alloc("W_dec", (F, d)), "b_enc": g.alloc("b_enc", (F,))}
+        # parameters + gradient matrices: one NVSwitch multicast pool when the fabric offers it (multimem.ld_reduce / multimem.st in
+        # p2p.cu), else IPC-shared cudaMalloc buffers (peer loads / stores).  The dense 3xTF32 encoder needs its residual plane
+        # all-gathered too and stays on the peer path.
+        big = ("W_encT", "W_dec", "gW_dec", "gW_encT")
+        self.mc = None
+        pool = None
+        fused_geometry = d % 4 == 0 and d >= 32 and F % 128 == 0 and k <= 48 and F <= 131072      # SaeStepEngine's fused-encoder rule
+        if fused_geometry and kw.get("encoder", "auto") != "dense" and kw.get("gemm_impl", L.GEMM_AUTO) == L.GEMM_AUTO:
+            rowb = -(-F // 64) * 256                                   # b_enc, padded to 256 bytes
+            pool = g.try_multicast_pool(4 * F * d * 4 + rowb)
+        if pool is not None:
+            own, mcp, _size = pool
+            offs = {name: i * F * d * 4 for i, name in enumerate(big)}
+            offs["b_enc"] = 4 * F * d * 4
+            shared = {}
+            for name in big + ("b_enc",):
+                shape = (F, d) if name != "b_enc" else (F,)
+                t = torch.as_tensor(_RawCuda(own + offs[name], shape, "<f4"), device=g.device)
+                g.local[name], g.peer_ptr[name] = t, [own + offs[name] if r == g.rank else 0 for r in range(g.world)]
+                shared[name] = t
+            self.mc = {name: mcp + offs[name] for name in offs}
+        else:
+            shared = {"W_encT": g.alloc("W_encT", (F, d)), "W_dec": g.alloc("W_dec", (F, d)), "b_enc": g.alloc("b_enc", (F,))}
+            for name in ("gW_dec", "gW_encT"):
+                g.alloc(name, (F, d))
         shared["W_encT"].copy_(W_encT)
         shared["W_dec"].copy_(W_dec)
         shared["b_enc"].copy_(b_enc)
-        for name, shape in (("gW_dec", (F, d)), ("gW_encT", (F, d)), ("gb_enc", (F,)), ("gb_dec", (d,)), ("fired", (F,)), ("xsum", (d,)),
-                            ("norm_parts", (MAX_RANKS,))):
+        for name, shape in (("gb_enc", (F,)), ("gb_dec", (d,)), ("fired", (F,)), ("xsum", (d,)), ("norm_parts", (MAX_RANKS,))):
             g.alloc(name, shape)
         g.alloc("flags", (MAX_RANKS,), dtype=torch.int32)
         super().__init__(shared["W_encT"], shared["W_dec"], shared["b_enc"], b_dec.clone().contiguous(), k, **kw)
@@ -165,7 +270,18 @@ class SaeDPEngine(SaeStepEngine):
         s.m_dec, s.v_dec, s.m_enc, s.v_enc = p(self.m_dec), p(self.v_dec), p(self.m_enc), p(self.v_enc)
         s.m_be, s.v_be, s.m_bd, s.v_bd = p(self.m_be), p(self.v_be), p(self.m_bd), p(self.v_bd)
         s.since_fired, s.act_freq = p(since_fired), p(act_freq)
+        if self.mc is not None:
+            s.mc_gW_dec, s.mc_gW_encT = self.mc["gW_dec"], self.mc["gW_encT"]
+            s.mc_W_dec, s.mc_W_encT, s.mc_b_enc = self.mc["W_dec"], self.mc["W_encT"], self.mc["b_enc"]
         return s
+
+    def describe_exchange(self) -> str:
+        n = self.group.world
+        if self.mc is not None:
+            return (f"NVSwitch multicast: reduce-scatter by multimem.ld_reduce (summed in the switch), all-gather by multimem.st; "
+                    f"{int(2 * 8 * self.d * self.F / n / 1e6)} MB over NVLink per GPU per step")
+        return (f"peer loads / stores over NVLink: {int((n - 1) / n * (2 * self.d * self.F * 4 * 2) / 1e6)} MB per GPU per step"
+                + (f" ({getattr(self.group, 'multicast_note', '')})" if getattr(self.group, "multicast_note", "") else ""))
 
     @torch.no_grad()
     def train_step(self, x: torch.Tensor, lr: float, since_fired=None, act_freq=None, want_out: bool = False) -> torch.Tensor:
