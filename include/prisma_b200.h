@@ -236,6 +236,8 @@ typedef struct {
   /* [2] max_f ||W_encT[f,:]||_2 and max_f ||W_encT[f,:] - tf32_trunc(.)||_2 AFTER this step's update, for the fused encoder's error bound
    * (pb_sae_encode_topk_fused); may be NULL                                                                               */
   float* enc_norm_max;
+  /* 1: pb_sae_step_reset already zeroed gcol / gbdec2 / the work header for this step (pb_sae_backward then skips its memsets) */
+  int32_t pre_zeroed;
 } PbSaeStep;
 
 /* sae_in = norm_in(x) - b_dec (+ tf32 residual, row mean / std, column sums of x) -- sae.py:78-87, 557-566 */
@@ -249,6 +251,9 @@ PB_API int pb_sae_topk(const float* hidden_pre, int32_t rows, int32_t F, int32_t
 /* dense feature_acts [rows][F] = zeros.scatter_(idx, relu(val)) (sae.py:806-808) -- only for callers that need the dense tensor */
 PB_API int pb_sae_scatter_acts(const int32_t* idx, const float* val, float* dense, int32_t rows, int32_t k, int32_t F,
                                int32_t relu, pb_stream_t stream);
+/* one launch that zeroes the step's accumulators: feat_count [F], scalars [8], gcol / gbdec2 [d], the header of `work`, and
+ * fb_count [2] of the fused encoder (may be NULL)                                                                         */
+PB_API int pb_sae_step_reset(const PbSaeStep* s, int32_t* fb_count, pb_stream_t stream);
 /* sparse decode + normalised-MSE partials (+ g = dL/d(decoder output) and d(loss)/d(selected pre-activations) when training) */
 PB_API int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream);
 /* per-feature gradients of W_dec / W_enc / b_enc / b_dec, global grad norm, clip coefficient */
@@ -274,7 +279,7 @@ typedef struct {
   int32_t rows, d, F, k;
   int32_t c_keep;               /* 4, 6 or 8 keys kept per (token, 128-feature segment)                                   */
   int32_t m_cand;               /* candidates re-evaluated exactly per token in the first round: k <= m_cand <= 128       */
-  int32_t phases;               /* bit mask 1 | 2 | 4 (0 = all)                                                           */
+  int32_t phases;               /* bit mask 1 | 2 | 4 (0 = all); + 8: fb_count was zeroed by the caller (pb_sae_step_reset) */
   float err_coef;               /* safety factor on the error bound; <= 0: default 1.05                                   */
   const float* sae_in;          /* [rows][d]                                                                              */
   const float* W_encT;          /* [F][d] feature-major encoder                                                           */

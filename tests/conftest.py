@@ -9,6 +9,9 @@ for p in (ROOT, os.path.join(ROOT, "vit-prisma_b200")):
         sys.path.insert(0, p)
 
 
+collect_ignore = [os.path.join("golden", "ref_tests")]     # verbatim reference test files: run only through test_reference_suite_verbatim_gpu.py
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with `-m gpu` under gpurun)")
 

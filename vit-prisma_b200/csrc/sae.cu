@@ -235,11 +235,18 @@ __global__ void __launch_bounds__(256) k_sae_decode(const float* __restrict__ x,
       if (c4 < nvec) ld4(b_dec + 4 * c4, acc[i]);
       else acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     }
-    for (int j = 0; j < k; ++j) {
-      const float a = fmaxf(vr[j], 0.f);
-      if (a > 0.f) {
-        pos_part += 1.f;
-        const float* wr = W_dec + (int64_t)ir[j] * d;
+    // The k decoder rows of a token are independent gathers (L2 latency each): the support is read 32 entries at a time into lanes
+    // and broadcast, and the row loop is unrolled so several rows' loads are in flight.  A selected value that is not positive
+    // contributes a = 0 (its row is still read: rare, and it keeps the loop free of data-dependent branches).
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int jn = min(32, k - j0);
+      const int my_i = lane < jn ? ir[j0 + lane] : 0;
+      const float my_a = lane < jn ? fmaxf(vr[j0 + lane], 0.f) : 0.f;
+      pos_part += (float)__popc(__ballot_sync(0xffffffffu, my_a > 0.f));
+#pragma unroll 4
+      for (int j = 0; j < jn; ++j) {
+        const float a = __shfl_sync(0xffffffffu, my_a, j);
+        const float* wr = W_dec + (int64_t)__shfl_sync(0xffffffffu, my_i, j) * d;
 #pragma unroll
         for (int i = 0; i < CHUNKS; ++i) {
           const int c4 = i * 32 + lane;
@@ -293,10 +300,15 @@ __global__ void __launch_bounds__(256) k_sae_decode(const float* __restrict__ x,
         for (int q = 0; q < 4; ++q) e[i][q] *= gs;
         if (c4 < nvec) st4(g_out + (int64_t)row * d + 4 * c4, e[i]);
       }
-      for (int j = 0; j < k; ++j) {
-        float dot = 0.f;
-        if (vr[j] > 0.f) {
-          const float* wr = W_dec + (int64_t)ir[j] * d;
+      for (int j0 = 0; j0 < k; j0 += 32) {
+        const int jn = min(32, k - j0);
+        const int my_i = lane < jn ? ir[j0 + lane] : 0;
+        const bool my_on = lane < jn && vr[j0 + lane] > 0.f;      // ReLU backward on the TopK support
+        float my_dot = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < jn; ++j) {
+          const float* wr = W_dec + (int64_t)__shfl_sync(0xffffffffu, my_i, j) * d;
+          float dot = 0.f;
 #pragma unroll
           for (int i = 0; i < CHUNKS; ++i) {
             const int c4 = i * 32 + lane;
@@ -308,8 +320,9 @@ __global__ void __launch_bounds__(256) k_sae_decode(const float* __restrict__ x,
             }
           }
           dot = warp_sum(dot);
+          if (lane == j) my_dot = dot;
         }
-        if (lane == 0) dval[(int64_t)row * k + j] = dot;
+        if (lane < jn) dval[(int64_t)row * k + j0 + lane] = my_on ? my_dot : 0.f;
       }
     }
   }
@@ -847,7 +860,8 @@ k_sae_adam_bulk(float* __restrict__ W_dec, float* __restrict__ W_encT, float* __
                 const float* __restrict__ gW_encT, const float* __restrict__ gb_enc, float* __restrict__ m_dec, float* __restrict__ v_dec,
                 float* __restrict__ m_enc, float* __restrict__ v_enc, float* __restrict__ m_be, float* __restrict__ v_be,
                 const float* __restrict__ fired, float* __restrict__ since_fired, float* __restrict__ act_freq,
-                const SaeScalars* __restrict__ sc, AdamHyper h, int F, int d, int renorm, float* __restrict__ enc_norm_max, int S) {
+                const SaeScalars* __restrict__ sc, AdamHyper h, int F, int d, int renorm, float* __restrict__ enc_norm_max, int S,
+                float* __restrict__ b_dec, const float* __restrict__ gb_dec, float* __restrict__ m_bd, float* __restrict__ v_bd) {
   extern __shared__ __align__(128) unsigned char ab_smem[];
   const uint32_t s0 = smem_u32(ab_smem);
   const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = 8u * row_bytes;
@@ -863,6 +877,15 @@ k_sae_adam_bulk(float* __restrict__ W_dec, float* __restrict__ W_encT, float* __
   }
   __syncthreads();
   if (warp == 0) {
+    if (blockIdx.x == 0 && b_dec) {                 // the decoder bias (d values): this warp, before it turns producer
+      const float clip0 = sc->clip_coef;
+      for (int c = lane; c < d; c += 32) {
+        float mm = m_bd[c], vv = v_bd[c];
+        b_dec[c] = adam_update(b_dec[c], gb_dec[c] * clip0, mm, vv, h);
+        m_bd[c] = mm;
+        v_bd[c] = vv;
+      }
+    }
     if (lane == 0) {
       for (int i = 0; i < n_mine; ++i) {
         const int s = i % S;
@@ -1155,6 +1178,29 @@ __global__ void k_sae_fwd_scalars(SaeScalars* sc, float inv_elems, float inv_row
   sc->l0 = sc->pos_count * inv_rows;
 }
 
+// every accumulator a training step starts from zero, in one launch (they were six memsets / fills on the stream)
+__global__ void __launch_bounds__(256) k_sae_step_reset(float* __restrict__ feat_count, int F, float* __restrict__ scalars, float* __restrict__ gcol,
+                                                        float* __restrict__ gbdec2, int d, int* __restrict__ work_hdr, int* __restrict__ fb_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int f = i; f < F; f += gridDim.x * blockDim.x) feat_count[f] = 0.f;
+  if (i < d) { gcol[i] = 0.f; gbdec2[i] = 0.f; }
+  if (i < 8) scalars[i] = 0.f;
+  if (i < 4 && work_hdr) work_hdr[i] = 0;
+  if (i < 2 && fb_count) fb_count[i] = 0;
+}
+
+extern "C" int pb_sae_step_reset(const PbSaeStep* s, int32_t* fb_count, pb_stream_t stream) {
+  PB_CHECK_ARG(s && s->feat_count && s->scalars && s->gcol && s->gbdec2, "pb_sae_step_reset: missing pointers");
+  PB_CHECK_ARG(!s->work || s->work_bytes >= (int64_t)sizeof(SaeWorkHeader), "pb_sae_step_reset: work buffer too small");
+  const int n = s->F > s->d ? s->F : s->d;
+  int grid = (n + 255) / 256;
+  if (grid > pb_sm_count() * 2) grid = pb_sm_count() * 2;
+  if (grid * 256 < s->d) grid = (s->d + 255) / 256;
+  k_sae_step_reset<<<grid, 256, 0, (cudaStream_t)stream>>>(s->feat_count, s->F, (float*)s->scalars, s->gcol, s->gbdec2, s->d, (int*)s->work, fb_count);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
 extern "C" int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream) {
   PB_CHECK_ARG(s && s->x && s->xsum && s->idx && s->val && s->W_dec && s->b_dec && s->scalars, "pb_sae_decode: missing pointers");
   PB_CHECK_ARG(!s->training || (s->g && s->dval), "pb_sae_decode: training needs g and dval buffers");
@@ -1184,8 +1230,10 @@ extern "C" int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream) {
   const int64_t n = (int64_t)s->rows * s->k;
   k_csc_fill<<<pb_sm_count() * 4, 256, 0, st>>>(s->idx, s->csc_cursor, s->csc_entries, n);
   PB_LAUNCH_CHECK();
-  PB_CUDA(cudaMemsetAsync(s->gcol, 0, sizeof(float) * d, st));
-  PB_CUDA(cudaMemsetAsync(s->gbdec2, 0, sizeof(float) * d, st));
+  if (!s->pre_zeroed) {
+    PB_CUDA(cudaMemsetAsync(s->gcol, 0, sizeof(float) * d, st));
+    PB_CUDA(cudaMemsetAsync(s->gbdec2, 0, sizeof(float) * d, st));
+  }
   const int rpc = 32;
   k_colsum<<<(s->rows + rpc - 1) / rpc, 256, 0, st>>>(s->g, s->gcol, s->rows, d, rpc);
   PB_LAUNCH_CHECK();
@@ -1197,7 +1245,7 @@ extern "C" int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream) {
   SaeWorkHeader* wh = (SaeWorkHeader*)s->work;
   int* work_feats = (int*)(wh + 1);
   int* work_chunks = work_feats + F;
-  PB_CUDA(cudaMemsetAsync(wh, 0, sizeof(SaeWorkHeader), st));
+  if (!s->pre_zeroed) PB_CUDA(cudaMemsetAsync(wh, 0, sizeof(SaeWorkHeader), st));
   const int grid = persistent_grid(8, F);
   PB_DISPATCH_CHUNKS(ch, (k_sae_grads<C_><<<grid, 256, sizeof(float) * d, st>>>(s->csc_off, s->csc_entries, s->val, s->dval, s->g, s->sae_in,
                                                                                 s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc, s->gbdec2,
@@ -1252,7 +1300,7 @@ extern "C" int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream) {
     PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                     \
     kern<<<g2, AB_THREADS, smem, st>>>(s->W_dec, s->W_encT, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc, s->m_dec, s->v_dec, s->m_enc, \
                                        s->v_enc, s->m_be, s->v_be, s->fired, s->since_fired, s->act_freq, (const SaeScalars*)s->scalars, \
-                                       h, F, d, s->renorm_decoder, s->enc_norm_max, S);                                              \
+                                       h, F, d, s->renorm_decoder, s->enc_norm_max, S, s->b_dec, s->gb_dec, s->m_bd, s->v_bd);         \
   } while (0)
       switch (ch) {
         case 1: PB_ADAM_BULK(1); break;
@@ -1264,8 +1312,6 @@ extern "C" int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream) {
         default: pb_set_error("sae: d_in=%d unsupported", d); return PB_EUNSUPPORTED;
       }
 #undef PB_ADAM_BULK
-      PB_LAUNCH_CHECK();
-      k_sae_adam_vec<<<(d + 255) / 256, 256, 0, st>>>(s->b_dec, s->gb_dec, s->m_bd, s->v_bd, (const SaeScalars*)s->scalars, h, d);
       PB_LAUNCH_CHECK();
       return PB_OK;
     }

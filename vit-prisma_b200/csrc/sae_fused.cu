@@ -580,14 +580,14 @@ extern "C" int pb_sae_encode_topk_fused(const PbSaeEncode* e, pb_stream_t stream
   PB_CHECK_ARG(e->cand_bytes >= (int64_t)e->rows * nkeys * 4, "pb_sae_encode_topk_fused: candidate buffer too small");
   if (e->rows == 0) return PB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int phases = e->phases ? e->phases : 7;
+  const int phases = (e->phases & 7) ? e->phases : (e->phases | 7);
   if (phases & 1) {
     if (e->c_keep == 4) PB_TRY(launch_enc_cand<4>(e, st));
     else if (e->c_keep == 6) PB_TRY(launch_enc_cand<6>(e, st));
     else PB_TRY(launch_enc_cand<8>(e, st));
   }
   if (phases & 2) {
-    PB_CUDA(cudaMemsetAsync(e->fb_count, 0, 2 * sizeof(int), st));    // [0] rows on the exact path, [1] candidates re-scored (proven rows)
+    if (!(phases & 8)) PB_CUDA(cudaMemsetAsync(e->fb_count, 0, 2 * sizeof(int), st));    // [0] rows on the exact path, [1] candidates re-scored
     const float coef = e->err_coef > 0.f ? e->err_coef : 1.05f;       // safety factor on the Cauchy-Schwarz bound (norms evaluated in fp32)
     const int nseg = e->F / FZ_SEG, spt = (nseg + 255) / 256;
     if (spt <= 1) PB_TRY(launch_select<1>(e, nseg, coef, st));

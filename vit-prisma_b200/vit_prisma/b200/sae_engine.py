@@ -34,7 +34,7 @@ class PbSaeStep(C.Structure):
             "csc_off", "csc_cursor", "csc_entries", "gW_dec", "gW_encT", "gb_enc", "gb_dec", "gcol", "gbdec2",
             "fired", "scalars", "m_dec", "v_dec", "m_enc", "v_enc", "m_be", "v_be", "m_bd", "v_bd",
             "since_fired", "act_freq")]
-        + [("global_rows", i32), ("dist", i32), ("work", vp), ("work_bytes", i64), ("enc_norm_max", vp)]
+        + [("global_rows", i32), ("dist", i32), ("work", vp), ("work_bytes", i64), ("enc_norm_max", vp), ("pre_zeroed", i32)]
     )
 
 
@@ -52,6 +52,7 @@ L.register_signatures({
     "pb_sae_prep": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "pb_sae_topk": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, i64, vp]),
     "pb_sae_scatter_acts": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "pb_sae_step_reset": (i32, [C.POINTER(PbSaeStep), vp, vp]),
     "pb_sae_decode": (i32, [C.POINTER(PbSaeStep), vp]),
     "pb_sae_backward": (i32, [C.POINTER(PbSaeStep), vp]),
     "pb_sae_adam": (i32, [C.POINTER(PbSaeStep), vp]),
@@ -247,8 +248,9 @@ class SaeStepEngine:
         g.bias, g.out0, g.ld0 = self.b_enc.data_ptr(), self.hidden_pre.data_ptr(), self.F
         L.check(lib.pb_gemm(C.byref(g), st), "pb_gemm(encoder)")
 
-    def encode_topk(self, x: torch.Tensor) -> None:
-        """prep + encoder GEMM + topk; fills sae_in, mu, sd, xsum, hidden_pre, idx, val, feat_count."""
+    def encode_topk(self, x: torch.Tensor, pre_zeroed: bool = False) -> None:
+        """prep + encoder GEMM + topk; fills sae_in, mu, sd, xsum, hidden_pre, idx, val, feat_count.
+        ``pre_zeroed``: the caller already ran ``pb_sae_step_reset`` (feat_count and fb_count are zero)."""
         lib, st = L.get_lib(), _stream()
         rows = x.shape[0]
         self._ensure_rows(rows)
@@ -256,9 +258,10 @@ class SaeStepEngine:
                                 self.sae_in_lo.data_ptr() if (self.sae_in_lo is not None and self.gemm_impl != L.GEMM_SIMT) else None,
                                 self.mu.data_ptr(), self.sd.data_ptr(),
                                 self.xsum.data_ptr(), rows, self.d, self.norm_mode, st), "pb_sae_prep")
-        self.feat_count.zero_()
+        if not pre_zeroed:
+            self.feat_count.zero_()
         if self.encoder == "fused":
-            L.check(lib.pb_sae_encode_topk_fused(C.byref(self._enc_desc(rows)), st), "pb_sae_encode_topk_fused")
+            L.check(lib.pb_sae_encode_topk_fused(C.byref(self._enc_desc(rows, 8 if pre_zeroed else 0)), st), "pb_sae_encode_topk_fused")
             return
         self._encoder_gemm(rows)
         scratch = self.topk_scratch
@@ -284,10 +287,12 @@ class SaeStepEngine:
         _need_cuda(x)
         x = x.contiguous().float()
         lib, st = L.get_lib(), _stream()
-        self.encode_topk(x)
-        self.scalars.zero_()
+        self._ensure_rows(x.shape[0])
         self.step_count += 1
         s = self._desc(x, training=True, lr=float(lr), since_fired=since_fired, act_freq=act_freq, want_out=want_out)
+        s.pre_zeroed = 1
+        L.check(lib.pb_sae_step_reset(C.byref(s), self.fb_count.data_ptr(), st), "pb_sae_step_reset")     # every accumulator of the step, one launch
+        self.encode_topk(x, pre_zeroed=True)
         L.check(lib.pb_sae_decode(C.byref(s), st), "pb_sae_decode")
         L.check(lib.pb_sae_backward(C.byref(s), st), "pb_sae_backward")
         L.check(lib.pb_sae_adam(C.byref(s), st), "pb_sae_adam")

@@ -16,6 +16,8 @@ reference ``HookedViT`` works unchanged (state-dict layout: SURVEY section 8b).
 """
 from __future__ import annotations
 
+import contextlib
+
 import logging
 import os
 from contextlib import contextmanager
@@ -25,6 +27,7 @@ import torch
 import torch.nn as nn
 
 from vit_prisma.b200 import ops
+from vit_prisma.b200._lib import PrismaB200Error
 from vit_prisma.b200.vit_engine import VitEngine, fusable_reason
 from vit_prisma.configs.HookedViTConfig import HookedViTConfig
 from vit_prisma.models.layers.attention import Attention
@@ -107,9 +110,58 @@ class HookedViT(HookedRootModule):
                 return f"torch hook registered on {getattr(mod, 'name', type(mod).__name__)}"
         return None
 
+    # ----------------------------------------------------------------- host-resident models
+    # Device policy.  Every arithmetic operation of this package runs on the GPU; there is no CPU compute path.  A module whose
+    # parameters live in host memory (the reference's default: ``HookedViTConfig.device = "cpu"``, which its own offline tests
+    # rely on) is therefore *staged*: for the duration of a call its parameters and buffers point at cached device copies
+    # (refreshed when a parameter's version counter or storage changes), the input is copied host -> device, the same CUDA
+    # kernels run, and the output / cache entries are copied back to the input's device.  Hook functions see device tensors.
+    # That is two memcpys around the GPU path -- data movement, not a fallback; without a CUDA device the call raises.
+    def _host_resident(self) -> bool:
+        return not self.cls_token.is_cuda
+
+    @contextlib.contextmanager
+    def _staged_on_gpu(self):
+        if not torch.cuda.is_available():
+            raise PrismaB200Error("prisma_b200: this model lives in host memory and no CUDA device is visible -- the hot path is "
+                                  "hand-written sm_100a CUDA and has no CPU fallback")
+        cache = self.__dict__.setdefault("_stage_cache", {})
+        swapped = []
+        for name, t in list(self.named_parameters()) + list(self.named_buffers()):
+            if t.is_cuda:
+                continue
+            key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+            hit = cache.get(name)
+            if hit is None or hit[0] != key:
+                hit = (key, t.data.to("cuda", non_blocking=False))
+                cache[name] = hit
+            swapped.append((t, t.data))
+            t.data = hit[1]
+        prev_device = self.cfg.device
+        self.cfg.device = "cuda"
+        try:
+            yield
+        finally:
+            for t, host in swapped:
+                t.data = host
+            self.cfg.device = prev_device
+
+    @staticmethod
+    def _to_like(obj, device):
+        if isinstance(obj, torch.Tensor):
+            return obj.to(device)
+        if isinstance(obj, tuple):
+            return tuple(HookedViT._to_like(o, device) for o in obj)
+        return obj
+
     # ----------------------------------------------------------------- forward
     def forward(self, input: torch.Tensor, stop_at_layer: Optional[int] = None):
         """``stop_at_layer`` (exclusive, negative allowed) returns the residual stream after that many blocks."""
+        if isinstance(input, torch.Tensor) and self._host_resident():
+            with self._staged_on_gpu():
+                return self.forward(input.to("cuda"), stop_at_layer).to(input.device)
+        if isinstance(input, torch.Tensor) and not input.is_cuda:
+            input = input.to(self.cls_token.device)                 # device-resident model, host input: one H2D copy
         why = self._fused_blocker(input)
         if why is None:
             self.last_route = "fused"
@@ -167,6 +219,16 @@ class HookedViT(HookedRootModule):
     def _run_with_cache_impl(self, *model_args, names_filter=None, device=None, remove_batch_dim=False,
                              incl_bwd=False, reset_hooks_end=True, clear_contexts=False, fwd_hooks=[],
                              bwd_hooks=[], **model_kwargs):
+        if model_args and isinstance(model_args[0], torch.Tensor) and self._host_resident():
+            home = model_args[0].device                              # host-resident model: stage, run on the GPU, bring results home
+            with self._staged_on_gpu():
+                out, cache = self._run_with_cache_impl(model_args[0].to("cuda"), *model_args[1:], names_filter=names_filter,
+                                                       device=device if device is not None else home, remove_batch_dim=remove_batch_dim,
+                                                       incl_bwd=incl_bwd, reset_hooks_end=reset_hooks_end, clear_contexts=clear_contexts,
+                                                       fwd_hooks=fwd_hooks, bwd_hooks=bwd_hooks, **model_kwargs)
+            return self._to_like(out, home), cache
+        if model_args and isinstance(model_args[0], torch.Tensor) and not model_args[0].is_cuda:
+            model_args = (model_args[0].to(self.cls_token.device),) + tuple(model_args[1:])
         plain = (len(model_args) == 1 and not incl_bwd and not fwd_hooks and not bwd_hooks
                  and set(model_kwargs) <= {"stop_at_layer"})
         why = self._fused_blocker(model_args[0]) if plain else "user hooks / backward requested"
