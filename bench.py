@@ -670,7 +670,7 @@ def dp_parity_gate(ctx):
         return True, f"skipped: batch {B} / d_sae {F} not divisible by {world}"
     per = B // world
     cfg = sae_runner_cfg(d, F // d, k, per, lr=gold["lr"], normalize_activations=gold["norm"], b_dec_init_method="zeros")
-    trainer = build_sae_trainer(ctx, cfg, store=None, group=P2PGroup(rank, world, dev), init=gold["init"])
+    trainer = build_sae_trainer(ctx, cfg, store=object(), group=P2PGroup(rank, world, dev), init=gold["init"])   # batches are fed by hand below
     trainer.enable_data_parallel_if_requested()
     sae = trainer.sparse_coder
     eng = sae.step_engine()

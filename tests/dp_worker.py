@@ -72,7 +72,7 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"DP_RESULT world={world} ok={bool(flag.item())} worst_param_rel_err={worst:.2e}", flush=True)
+        print(f"DP_RESULT world={world} ok={bool(flag.item())} worst_param_rel_err={worst:.2e} exchange: {eng.describe_exchange()}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)

@@ -21,3 +21,4 @@ def test_dp_training_matches_single_process_reference(world):
     tail = (out.stdout + out.stderr)[-3000:]
     assert out.returncode == 0, tail
     assert f"DP_RESULT world={world} ok=True" in out.stdout, tail
+    print([ln for ln in out.stdout.splitlines() if ln.startswith("DP_RESULT")])

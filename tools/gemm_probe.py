@@ -28,7 +28,12 @@ def probe(M, N, K, dtype, variants):
         elif name == "simt": fn = lambda: ops.gemm(a, w, b, out0=o0, impl=L.GEMM_SIMT)
         elif name == "torch": fn = lambda: torch.matmul(a, w.t(), out=o0)
         ms = timeit(fn)
-        print(f"{str(dtype):15s} M={M} N={N} K={K} {name:12s} {ms:8.3f} ms  {2.0*M*N*K/ms/1e9:8.1f} TFLOP/s", flush=True)
+        err = ""
+        if name in ("pre", "pre+resid") and os.environ.get("PROBE_CHECK"):       # numerics of the variant under test vs fp32 torch
+            ref = a.float() @ w.float().t() + b.float()
+            got = o0.float()
+            err = f"  max rel err {((got - ref).abs().max() / ref.abs().max()).item():.2e}"
+        print(f"{str(dtype):15s} M={M} N={N} K={K} {name:12s} {ms:8.3f} ms  {2.0*M*N*K/ms/1e9:8.1f} TFLOP/s{err}", flush=True)
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"

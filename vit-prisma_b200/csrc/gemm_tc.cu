@@ -667,6 +667,8 @@ int launch_tc2(const PbGemm* g, cudaStream_t st) {
   return PB_OK;
 }
 
+#include "gemm_tc_pair.cuh"
+
 }  // namespace
 
 // shape / alignment gate for the tensor-core path
@@ -691,11 +693,14 @@ int pb_gemm_tc(const PbGemm* g, cudaStream_t st) {
   static int variant = -1;  // PB_GEMM_TC_VARIANT=1 forces the one-tile-per-CTA kernel (A/B measurements)
   if (variant < 0) { const char* e = getenv("PB_GEMM_TC_VARIANT"); variant = e ? atoi(e) : 0; }
   if (g->dtype == PB_BF16) {
+    // variant 3: CTA pairs (cta_group::2), 256 x 256 per pair -- opt-in until it has been measured against variant 0 on every shape
+    if (variant == 3 && g->N >= 256 && g->M >= 256) return launch_tc2_pair<bf16, 1, 256, 6, 8>(g, st);
     if (variant != 1 && g->N >= 256) return launch_tc2<bf16, 1, 256, 4, 8>(g, st);
     if (variant != 1 && g->N >= 128) return launch_tc2<bf16, 1, 128, 4, 4>(g, st);
     return launch_tc<bf16, 1, 128, 3>(g, st);
   }
   if (variant == 2 && g->N >= 256) return launch_tc2<float, 3, 256, 2, 4>(g, st);   // wider tile, shallower ring (A/B)
+  if (variant == 3 && g->N >= 256 && g->M >= 256) return launch_tc2_pair<float, 3, 256, 3, 4>(g, st);
   if (variant != 1) return launch_tc2<float, 3, 128, 3, 4>(g, st);
   return launch_tc<float, 3, 128, 3>(g, st);
 }

@@ -1,9 +1,8 @@
-// wip/gemm_tc_2cta.cu -- DRAFT, NOT BUILT INTO libprisma_b200.so, NEVER RUN ON A GPU YET (round-1 GPU budget ended).
+// gemm_tc_pair.cuh -- CTA-pair (tcgen05 cta_group::2) variant of k_gemm_tc2; included by gemm_tc.cu inside its anonymous namespace.
 //
-// CTA-pair (cta_group::2) variant of k_gemm_tc2 for round 2.  Why: the persistent 128x256 kernel sits on the per-SM TMA ingest
-// limit (~46 B/clk/SM: bf16 plain 0.106 ms vs cuBLAS 0.096; fp32 3xTF32 at 77 % of its tensor bound, profiles/r01_gemm_notes.md).
-// A pair of CTAs on one TPC computes a 256 x BN tile with ONE tcgen05.mma.cta_group::2 stream issued by the leader: each CTA
-// loads its own 128 rows of A and HALF of the B tile, so the B bytes per SM halve (bf16 128x256: 590 -> 393 KB per tile).
+// Why: the persistent 128 x 256 kernel is limited by the per-SM operand ingest (bf16 plain GEMM 0.106 ms vs cuBLAS 0.096,
+// profiles/r01_gemm_notes.md).  A pair of CTAs on one TPC computes a 256 x BN tile with ONE tcgen05.mma.cta_group::2 stream issued by
+// the leader: each CTA loads its own 128 rows of A and HALF of the B tile, so the B bytes per SM halve.
 //
 // Protocol (differences from k_gemm_tc2 are marked [2CTA]):
 //   * __cluster_dims__(2,1,1); rank = %cluster_ctarank; rank 0 = leader.  A cluster walks tiles cluster_id, cluster_id + n_clusters ...
@@ -15,14 +14,10 @@
 //   * tempty[ab] lives in the leader, count 2*NEPI: every epilogue warp of either CTA arrives on it through mapa          [2CTA]
 //   * TMEM: tcgen05.alloc.cta_group::2 executed by warp 1 of both CTAs; each CTA's 128 lanes x (2*BN) columns hold ITS 128 rows.
 //   * teardown: cluster barrier before tcgen05.dealloc.cta_group::2                                                     [2CTA]
-// PTX forms taken from the CUTLASS headers vendored in this image (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_2D,
+// PTX forms follow the CUTLASS headers vendored in this image (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_2D,
 // cute/arch/mma_sm100_umma.hpp SM100_MMA_*_2x1SM_SS, cutlass/arch/barrier.h umma_arrive_multicast_2x1SM, ClusterBarrier::arrive).
-//
-// Compile check only:  nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 --expt-relaxed-constexpr -c wip/gemm_tc_2cta.cu
-// To try it: add this file to the build, route launch_tc2 -> launch_tc2_pair behind PB_GEMM_TC_VARIANT=3, run tests/test_ops_gpu.py -k tc.
-#include "../gemm_tc.cu"   // helpers, TcCfg / Tc2Cfg, epilogue (internal linkage; this TU is never linked with gemm_tc.o)
+#pragma once
 
-namespace {
 
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;            // shared::cluster address of the same offset in CTA rank 0 of the pair
 
@@ -282,8 +277,4 @@ int launch_tc2_pair(const PbGemm* g, cudaStream_t st) {
   return PB_OK;
 }
 
-// candidate configurations: bf16 256 x 256 per pair, 6 stages of 32 KB; fp32 (3xTF32) 256 x 256 per pair, 3 stages of 64 KB
-template int launch_tc2_pair<bf16, 1, 256, 6, 8>(const PbGemm*, cudaStream_t);
-template int launch_tc2_pair<float, 3, 256, 3, 4>(const PbGemm*, cudaStream_t);
 
-}  // namespace

@@ -841,10 +841,14 @@ __global__ void __launch_bounds__(256) k_sae_adam_rows(float* __restrict__ W_dec
 // k_sae_adam_rows keeps a feature's rows in registers: its loads are issued in four dependent waves per feature (w,g -> m,v ->
 // encoder row), 16 warps per SM, and it reaches 0.63 of the HBM copy bandwidth.  Here one producer lane streams every feature's
 // EIGHT rows (W_dec, gW_dec, m_dec, v_dec, W_encT, gW_encT, m_enc, v_enc: 8 x d x 4 bytes) into a shared-memory ring with
-// cp.async.bulk (completion on an mbarrier), AB_NW consumer warps update one feature each in place, and the six result rows go
+// cp.async.bulk (completion on an mbarrier), one consumer warp per ring slot updates its feature in place, and the six result rows go
 // back with cp.async.bulk stores.  The bytes in flight per SM are set by the ring depth (S x 24 KB at d = 768), not by registers.
-constexpr int AB_NW = 12;
-constexpr int AB_THREADS = 32 * (1 + AB_NW);
+// One consumer warp per ring slot (block = 32 x (1 + S) threads): iteration i and iteration i + S then belong to the SAME warp, so a
+// warp never waits for phase p + 1 of a slot's "full" barrier before it has itself consumed phase p.  (With more warps than slots a
+// warp could start waiting a whole phase early; mbarrier parity is one bit, the early waiter saw "already complete" and read a slot
+// another warp was still updating -- the first 12-warp version deadlocked in run r2d.)
+constexpr int AB_MAX_STAGES = 12;
+constexpr int AB_THREADS = 32 * (1 + AB_MAX_STAGES);
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
@@ -909,7 +913,7 @@ k_sae_adam_bulk(float* __restrict__ W_dec, float* __restrict__ W_encT, float* __
   const int nvec = d >> 2;
   const float clip = sc->clip_coef;
   float enc_best = 0.f, enc_best_lo = 0.f;
-  for (int i = warp - 1; i < n_mine; i += AB_NW) {
+  for (int i = warp - 1; i < n_mine; i += S) {
     const int s = i % S;
     const uint32_t ph = (uint32_t)(i / S) & 1u;
     const int f = blockIdx.x + i * gridDim.x;
@@ -1298,7 +1302,7 @@ extern "C" int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream) {
   do {                                                                                                                                \
     auto kern = k_sae_adam_bulk<CH>;                                                                                                  \
     PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                     \
-    kern<<<g2, AB_THREADS, smem, st>>>(s->W_dec, s->W_encT, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc, s->m_dec, s->v_dec, s->m_enc, \
+    kern<<<g2, 32 * (1 + S), smem, st>>>(s->W_dec, s->W_encT, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc, s->m_dec, s->v_dec, s->m_enc, \
                                        s->v_enc, s->m_be, s->v_be, s->fired, s->since_fired, s->act_freq, (const SaeScalars*)s->scalars, \
                                        h, F, d, s->renorm_decoder, s->enc_norm_max, S, s->b_dec, s->gb_dec, s->m_bd, s->v_bd);         \
   } while (0)

@@ -27,7 +27,8 @@ import torch
 import torch.nn as nn
 
 from vit_prisma.b200 import ops
-from vit_prisma.b200._lib import PrismaB200Error
+from vit_prisma.b200._lib import PrismaB200Error  # noqa: F401
+from vit_prisma.b200.staging import _move, host_staged, staged_on_gpu
 from vit_prisma.b200.vit_engine import VitEngine, fusable_reason
 from vit_prisma.configs.HookedViTConfig import HookedViTConfig
 from vit_prisma.models.layers.attention import Attention
@@ -111,48 +112,17 @@ class HookedViT(HookedRootModule):
         return None
 
     # ----------------------------------------------------------------- host-resident models
-    # Device policy.  Every arithmetic operation of this package runs on the GPU; there is no CPU compute path.  A module whose
-    # parameters live in host memory (the reference's default: ``HookedViTConfig.device = "cpu"``, which its own offline tests
-    # rely on) is therefore *staged*: for the duration of a call its parameters and buffers point at cached device copies
-    # (refreshed when a parameter's version counter or storage changes), the input is copied host -> device, the same CUDA
-    # kernels run, and the output / cache entries are copied back to the input's device.  Hook functions see device tensors.
-    # That is two memcpys around the GPU path -- data movement, not a fallback; without a CUDA device the call raises.
+    # Device policy: vit_prisma/b200/staging.py.  A model whose parameters live in host memory (the reference's default
+    # ``HookedViTConfig.device = "cpu"``) is staged on the GPU for the duration of a call; nothing ever computes on the CPU.
     def _host_resident(self) -> bool:
         return not self.cls_token.is_cuda
 
-    @contextlib.contextmanager
     def _staged_on_gpu(self):
-        if not torch.cuda.is_available():
-            raise PrismaB200Error("prisma_b200: this model lives in host memory and no CUDA device is visible -- the hot path is "
-                                  "hand-written sm_100a CUDA and has no CPU fallback")
-        cache = self.__dict__.setdefault("_stage_cache", {})
-        swapped = []
-        for name, t in list(self.named_parameters()) + list(self.named_buffers()):
-            if t.is_cuda:
-                continue
-            key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
-            hit = cache.get(name)
-            if hit is None or hit[0] != key:
-                hit = (key, t.data.to("cuda", non_blocking=False))
-                cache[name] = hit
-            swapped.append((t, t.data))
-            t.data = hit[1]
-        prev_device = self.cfg.device
-        self.cfg.device = "cuda"
-        try:
-            yield
-        finally:
-            for t, host in swapped:
-                t.data = host
-            self.cfg.device = prev_device
+        return staged_on_gpu(self)
 
     @staticmethod
     def _to_like(obj, device):
-        if isinstance(obj, torch.Tensor):
-            return obj.to(device)
-        if isinstance(obj, tuple):
-            return tuple(HookedViT._to_like(o, device) for o in obj)
-        return obj
+        return _move(obj, device)
 
     # ----------------------------------------------------------------- forward
     def forward(self, input: torch.Tensor, stop_at_layer: Optional[int] = None):

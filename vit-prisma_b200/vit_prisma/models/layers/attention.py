@@ -16,6 +16,8 @@ from typing import Dict, Optional, Union
 
 import numpy as np
 import torch
+
+from vit_prisma.b200.staging import host_staged
 import torch.nn as nn
 
 from vit_prisma.b200 import ops
@@ -106,6 +108,7 @@ class Attention(nn.Module):
     def calculate_z_scores(self, v, pattern):
         return self.hook_z(ops.attn_pv(pattern, v))
 
+    @host_staged
     def forward(self, query_input, key_input, value_input, attention_mask=None) -> torch.Tensor:
         q, k, v = self.calculate_qkv_matrices(query_input, key_input, value_input)
         scores = self.hook_attn_scores(self.calculate_attn_scores(q, k, attention_mask))

@@ -4,6 +4,8 @@ from __future__ import annotations
 from typing import Dict, Union
 
 import torch
+
+from vit_prisma.b200.staging import host_staged
 import torch.nn as nn
 
 from vit_prisma.b200 import ops
@@ -24,6 +26,7 @@ class Head(nn.Module):
     def packed(self):
         return self._packs.get("wh", (self.W_H,), lambda: with_lo(pack_t(self.W_H)))
 
+    @host_staged
     def forward(self, residual: torch.Tensor) -> torch.Tensor:
         w, _ = self.packed()
         out, _ = ops.gemm(residual, w, self.b_H)

@@ -11,6 +11,8 @@ from __future__ import annotations
 from typing import Dict, Optional, Union
 
 import torch
+
+from vit_prisma.b200.staging import host_staged
 import torch.nn as nn
 
 from vit_prisma.b200 import ops
@@ -29,6 +31,7 @@ class _HookedNorm(nn.Module):
         self.hook_scale = HookPoint()        # [batch, pos, 1]
         self.hook_normalized = HookPoint()   # [batch, pos, length]
 
+    @host_staged
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         w = self.w if self.has_affine else None
         b = self.b if self.has_affine else None

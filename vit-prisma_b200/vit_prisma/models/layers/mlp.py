@@ -8,6 +8,8 @@ from __future__ import annotations
 from typing import Dict, Union
 
 import torch
+
+from vit_prisma.b200.staging import host_staged
 import torch.nn as nn
 
 from vit_prisma.b200 import ops
@@ -47,6 +49,7 @@ class MLP(nn.Module):
     def packed_out(self):
         return self._packs.get("wout", (self.W_out,), lambda: with_lo(pack_t(self.W_out)))
 
+    @host_staged
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         win, _ = self.packed_in()
         wout, _ = self.packed_out()

@@ -8,6 +8,8 @@ shapes (``embed.proj.weight [d, C, P, P]``, ``embed.proj.bias [d]``) are unchang
 from __future__ import annotations
 
 import torch
+
+from vit_prisma.b200.staging import host_staged
 import torch.nn as nn
 
 from vit_prisma.b200 import ops
@@ -25,6 +27,7 @@ class PatchEmbedding(nn.Module):
         if self.logger:
             self.logger.info(f"{stage} size: {tensor.shape}")
 
+    @host_staged
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self._log("PatchEmbedding input", x)
         B = x.shape[0]
@@ -48,5 +51,6 @@ class TubeletEmbedding(nn.Module):
         size = [cfg.video_tubelet_depth, cfg.patch_size, cfg.patch_size]
         self.proj = nn.Conv3d(cfg.n_channels, cfg.d_model, kernel_size=size, stride=size, bias=True)
 
+    @host_staged
     def forward(self, x):
         raise NotImplementedError("TubeletEmbedding (video) is outside the B200 hot-path scope (SURVEY #6)")

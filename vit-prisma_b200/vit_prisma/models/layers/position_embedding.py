@@ -5,6 +5,8 @@ from __future__ import annotations
 from typing import Dict, Union
 
 import torch
+
+from vit_prisma.b200.staging import host_staged
 import torch.nn as nn
 
 from vit_prisma.configs.HookedViTConfig import HookedViTConfig
@@ -21,5 +23,6 @@ class PosEmbedding(nn.Module):
             n *= cfg.video_num_frames // cfg.video_tubelet_depth
         self.W_pos = nn.Parameter(torch.empty(n + 1 if cfg.use_cls_token else n, cfg.d_model, dtype=cfg.dtype))
 
+    @host_staged
     def forward(self, tokens: torch.Tensor) -> torch.Tensor:
         return self.W_pos.unsqueeze(0).expand(tokens.size(0), -1, -1)

@@ -15,6 +15,8 @@ from __future__ import annotations
 from typing import Dict, Optional, Union
 
 import torch
+
+from vit_prisma.b200.staging import host_staged
 import torch.nn as nn
 
 from vit_prisma.b200 import ops
@@ -75,6 +77,7 @@ class TransformerBlock(nn.Module):
             return True
         return ln.hook_scale.is_inert and ln.hook_normalized.is_inert
 
+    @host_staged
     def forward(self, resid_pre: torch.Tensor, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         cfg = self.cfg
         resid_pre = self.hook_resid_pre(resid_pre)
@@ -111,6 +114,7 @@ class TransformerBlock(nn.Module):
 class BertBlock(TransformerBlock):
     """Post-LN variant (reference :141-246); same hook points, LayerNorm applied after each residual add."""
 
+    @host_staged
     def forward(self, resid_pre: torch.Tensor, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         resid_pre = self.hook_resid_pre(resid_pre)
         attn_out = self.attn(query_input=resid_pre, key_input=resid_pre, value_input=resid_pre, attention_mask=attn_mask)
