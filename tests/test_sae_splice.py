@@ -67,3 +67,34 @@ def test_spliced_forward_equals_replacing_the_activation_by_hand():
     out_err, cache_err = model.run_with_cache_with_saes(x, saes=[sae], use_error_term=True)
     assert torch.allclose(out_err, clean, rtol=1e-5, atol=1e-6) and f"{name}.hook_sae_out" in cache_err
     assert model(x) is not None and model.last_route == "fused"
+
+
+@pytest.mark.gpu
+def test_substitution_loss_matches_the_spliced_model_and_the_oracle_clean_loss():
+    """get_substitution_loss (reference sae/evals/evals.py:321-391): clean loss vs the CPU oracle's forward, reconstruction loss vs the
+    HookedSAEViT splice of the same SAE, zero-ablation loss vs a hand-rolled hook, score = (zero - recons) / (zero - clean)."""
+    import torch.nn.functional as F
+    from oracle.vit_oracle import vit_forward_with_cache
+    from vit_prisma.sae.evals.evals import get_logits, get_similarity, get_substitution_loss, zero_ablate_hook
+    torch.manual_seed(3)
+    model = HookedSAEViT(HookedViTConfig(**VIT)).to("cuda").eval()
+    sae = _sae("cuda", layer=1)
+    sae.set_decoder_norm_to_unit_norm()
+    x = torch.randn(6, 3, 32, 32)
+    labels = torch.tensor([1, 4, 0, 9, 3, 3])
+    text = torch.nn.functional.normalize(torch.randn(10, VIT["n_classes"]), dim=-1)
+    score, loss, recons, zero = get_substitution_loss(sae, model, x, labels, text, device=torch.device("cuda"))
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    cfg = dict(VIT, n_channels=3, eps=model.cfg.eps, activation_name=model.cfg.activation_name, normalization_type=model.cfg.normalization_type,
+               use_cls_token=model.cfg.use_cls_token, layer_norm_pre=model.cfg.layer_norm_pre, normalize_output=model.cfg.normalize_output,
+               return_type=model.cfg.return_type, classification_type=model.cfg.classification_type)
+    ref_out, _ = vit_forward_with_cache(sd, cfg, x)
+    ref_loss = F.cross_entropy(ref_out @ text.T, labels)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
+    spliced = model.run_with_saes(x.cuda(), saes=[sae])
+    assert abs(float(recons) - float(F.cross_entropy(get_logits(spliced, text).float(), labels.cuda()))) <= 1e-5
+    zeroed = model.run_with_hooks(x.cuda(), fwd_hooks=[("blocks.1.hook_resid_post", zero_ablate_hook)])
+    assert abs(float(zero) - float(F.cross_entropy((zeroed.float() @ text.cuda().T), labels.cuda()))) <= 1e-5
+    assert abs(float(score) - float((zero - recons) / (zero - loss))) <= 1e-6
+    sm, top = get_similarity(spliced, text, k=3)
+    assert sm.shape == (6, 10) and top.shape == (6, 3) and torch.allclose(sm.sum(-1), torch.ones(6, device="cuda"), atol=1e-5)

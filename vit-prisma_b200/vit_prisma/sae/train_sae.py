@@ -17,7 +17,7 @@ Notes on fidelity
     ``set_decoder_norm_to_unit_norm()`` on the reference side);
   * ``optimizer`` / ``scheduler`` returned by ``initialize_training_variables`` are light handles (``param_groups[0]["lr"]``,
     ``step()``, ``get_last_lr()``) -- the optimizer state lives in the engine's device buffers;
-  * transcoders are not built yet and raise at construction (dense ReLU + L1, ghost grads and the Gated SAE are).
+  * transcoders (``cfg.is_transcoder``) train through ``vit_prisma/b200/sae_transcoder.py``: ``layer_acts[:, 0]`` is the input, ``[:, 1]`` the target.
 """
 from __future__ import annotations
 
@@ -71,9 +71,10 @@ class VisionSAETrainer:
                 setattr(cfg, attr, None)
         self.bad_run_check = bool(cfg.min_l0 and cfg.min_explained_variance)
         self.model = model
-        if self.is_transcoder:
-            raise NotImplementedError("Transcoder training is outside the round-1 B200 scope (SURVEY 8f f3)")
-        if cfg.architecture == "gated":
+        if self.is_transcoder:                                       # train_sae.py:73-75
+            from vit_prisma.sae.transcoder import Transcoder
+            self.sparse_coder = Transcoder(cfg)
+        elif cfg.architecture == "gated":
             self.sparse_coder = GatedSparseAutoencoder(cfg)
         elif cfg.architecture in ("standard", "vanilla"):
             self.sparse_coder = StandardSparseAutoencoder(cfg)
@@ -147,7 +148,7 @@ class VisionSAETrainer:
         if self.p2p_group is None or self.p2p_group.world == 1:
             return
         cfg = self.cfg
-        if cfg.architecture == "gated" or cfg.activation_fn_str != "topk" or cfg.use_ghost_grads:
+        if self.is_transcoder or cfg.architecture == "gated" or cfg.activation_fn_str != "topk" or cfg.use_ghost_grads:
             raise NotImplementedError("data-parallel SAE training over NVLink peer memory covers the TopK step (standard architecture, "
                                       "no ghost grads); the dense / ghost / gated steps run single-GPU")
         import torch.distributed as dist
@@ -161,7 +162,11 @@ class VisionSAETrainer:
         cfg = sparse_autoencoder.cfg
         layers = cfg.hook_point_layer if isinstance(cfg.hook_point_layer, list) else [cfg.hook_point_layer]
         layer_id = 0 if isinstance(cfg.hook_point_layer, list) else layers.index(cfg.hook_point_layer)
-        sae_in = layer_acts[:, layer_id, :]
+        target_activation = None
+        if self.is_transcoder:                                       # train_sae.py:299-301: input and target ride in one tensor
+            sae_in, target_activation = layer_acts[:, 0, :], layer_acts[:, 1, :]
+        else:
+            sae_in = layer_acts[:, layer_id, :]
         sparse_autoencoder.train()
         engine = sparse_autoencoder.step_engine()
         if engine.step_count == 0:
@@ -179,8 +184,11 @@ class VisionSAETrainer:
 
         lr = optimizer.param_groups[0]["lr"]
         l1_loss = None
-        gated = cfg.architecture == "gated"
-        if gated:                                                    # one encoder GEMM for gate + magnitude paths, sae_gated.py
+        gated = cfg.architecture == "gated" and not self.is_transcoder
+        if self.is_transcoder:                                       # dense products + skip matrix + second decoder bias, sae_transcoder.py
+            scalars = engine.train_step_transcoder(sae_in, target_activation, lr, since_fired=n_forward_passes_since_fired,
+                                                   act_freq=act_freq_scores)
+        elif gated:                                                    # one encoder GEMM for gate + magnitude paths, sae_gated.py
             scalars = engine.train_step_gated(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores)
         elif cfg.activation_fn_str == "relu":                        # dense products + L1 (+ ghost grads), sae_dense.py
             scalars = engine.train_step_dense(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores,
@@ -198,6 +206,10 @@ class VisionSAETrainer:
             l1_loss = engine.aux[0] * (engine.l1_coefficient / sae_in.shape[0])
             aux_loss = engine.aux[1] / float(sae_in.shape[0])
             loss = loss + l1_loss + aux_loss
+        elif self.is_transcoder:                                     # loss = mse (+ l1 for dense activations), transcoder.py:93-103
+            if cfg.activation_fn_str != "topk":
+                l1_loss = engine.aux[0] * (engine.l1_coefficient / sae_in.shape[0])
+                loss = loss + l1_loss
         elif hasattr(engine, "aux"):                                 # device-side: loss = mse + l1 + ghost (sae.py:628)
             ghost_loss = engine.aux[1] / float(sae_in.shape[0] * engine.d)
             if cfg.activation_fn_str != "topk":

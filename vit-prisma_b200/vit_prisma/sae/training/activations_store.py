@@ -61,9 +61,10 @@ class VisionActivationsStore:
             self.image_dataloader_eval_iter = self._eval_batch_stream(self.image_dataloader_eval, cfg.device)
         self.image_dataloader_iter = self._batch_stream(self.image_dataloader, cfg.device)
         if create_dataloader:
-            if cfg.is_transcoder:
-                raise NotImplementedError("transcoder activation pairs are outside the round-1 scope (SURVEY 8f f3)")
-            self.storage_buffer = self.get_buffer(cfg.n_batches_in_buffer)
+            if cfg.is_transcoder:                                 # (input, target) activation pairs, reference :216-222
+                self.storage_buffer, self.storage_buffer_out = self.get_buffer(cfg.n_batches_in_buffer // 2)
+            else:
+                self.storage_buffer = self.get_buffer(cfg.n_batches_in_buffer)
             self.dataloader = self.get_data_loader()
 
     @staticmethod
@@ -83,12 +84,11 @@ class VisionActivationsStore:
         hp = self.cfg.hook_point_layer
         return hp if isinstance(hp, list) else [hp]
 
-    @torch.no_grad()
-    def get_activations(self, batch_images: torch.Tensor) -> torch.Tensor:
-        """[b, T', n_layers, d_in] for the configured hook point(s) (reference :252-296)."""
-        layers = self._layers()
-        names = [self.cfg.hook_point.format(layer=layer) for layer in layers]
-        _, cache = self.model.run_with_cache(batch_images, names_filter=names, stop_at_layer=max(layers) + 1)
+    def _out_layers(self):
+        hp = self.cfg.out_hook_point_layer
+        return hp if isinstance(hp, list) else [hp]
+
+    def _pick(self, cache, names):
         per_layer = []
         for name in names:
             acts = cache[name]
@@ -99,18 +99,40 @@ class VisionActivationsStore:
             per_layer.append(acts)
         return torch.stack(per_layer, dim=2)
 
-    def get_buffer(self, n_batches_in_buffer: int) -> torch.Tensor:
+    @torch.no_grad()
+    def get_activations(self, batch_images: torch.Tensor):
+        """[b, T', n_layers, d_in] for the configured hook point(s) (reference :252-296); for a transcoder the pair
+        (input activations, target activations at ``cfg.out_hook_point``) from ONE run_with_cache call."""
+        layers = self._layers()
+        names = [self.cfg.hook_point.format(layer=layer) for layer in layers]
+        if not self.cfg.is_transcoder:
+            _, cache = self.model.run_with_cache(batch_images, names_filter=names, stop_at_layer=max(layers) + 1)
+            return self._pick(cache, names)
+        out_layers = self._out_layers()
+        out_names = [self.cfg.out_hook_point.format(layer=layer) for layer in out_layers]
+        _, cache = self.model.run_with_cache(batch_images, names_filter=names + out_names, stop_at_layer=max(max(layers), max(out_layers)) + 1)
+        return self._pick(cache, names), self._pick(cache, out_names)
+
+    def get_buffer(self, n_batches_in_buffer: int):
         cfg = self.cfg
         if cfg.use_cached_activations:
+            assert not cfg.is_transcoder, "Transcoder not supported with cached activations"       # reference :322
             return self._load_cached_activations(cfg.store_batch_size * n_batches_in_buffer, cfg.context_size, len(self._layers()), cfg.d_in)
-        chunks = []
+        chunks, chunks_out = [], []
         for _ in range(n_batches_in_buffer):
             acts = self.get_activations(next(self.image_dataloader_iter))
+            acts, acts_out = acts if cfg.is_transcoder else (acts, None)
             if cfg.use_patches_only:
                 acts = acts[:, 1:, :, :]
+                acts_out = None if acts_out is None else acts_out[:, 1:, :, :]
             chunks.append(acts.reshape(-1, acts.shape[2], cfg.d_in).to(cfg.dtype))
+            if acts_out is not None:
+                chunks_out.append(acts_out.reshape(-1, acts_out.shape[2], cfg.d_out).to(cfg.dtype))
         buf = torch.cat(chunks, dim=0)
-        return buf[torch.randperm(buf.shape[0], device=buf.device)]
+        perm = torch.randperm(buf.shape[0], device=buf.device)
+        if cfg.is_transcoder:
+            return buf[perm], torch.cat(chunks_out, dim=0)[perm]                 # the same permutation keeps the pairs together
+        return buf[perm]
 
     def _load_cached_activations(self, total_size, context_size, num_layers, d_in) -> torch.Tensor:
         """fp16/fp32 ``{idx}.pt`` shards of ``[tokens, n_layers, d_in]`` (reference :371-415)."""
@@ -148,6 +170,15 @@ class VisionActivationsStore:
 
     def get_data_loader(self) -> Iterator[Any]:
         half = self.cfg.n_batches_in_buffer // 2
+        if self.cfg.is_transcoder:                                   # reference :450-477: both halves shuffled with one permutation
+            new_in, new_out = self.get_buffer(half)
+            mix_in = torch.cat([new_in, self.storage_buffer], dim=0)
+            mix_out = torch.cat([new_out, self.storage_buffer_out], dim=0)
+            perm = torch.randperm(mix_in.shape[0], device=mix_in.device)
+            mix_in, mix_out = mix_in[perm], mix_out[perm]
+            keep = mix_in.shape[0] // 2
+            self.storage_buffer, self.storage_buffer_out = mix_in[:keep], mix_out[:keep]
+            return _ShuffledServer(torch.cat([mix_in[keep:], mix_out[keep:]], dim=1), self.cfg.train_batch_size)   # [tokens, 2, d]
         mixing = torch.cat([self.get_buffer(half), self.storage_buffer], dim=0)
         mixing = mixing[torch.randperm(mixing.shape[0], device=mixing.device)]
         keep = mixing.shape[0] // 2
