@@ -371,7 +371,7 @@ typedef struct {
   float* W_dec[PB_P2P_MAX_RANKS]; float* W_encT[PB_P2P_MAX_RANKS]; float* W_encT_lo[PB_P2P_MAX_RANKS]; float* b_enc[PB_P2P_MAX_RANKS];
   float* norm_parts[PB_P2P_MAX_RANKS]; uint32_t* flags[PB_P2P_MAX_RANKS];
   /* local only */
-  float *gb_enc_red, *gb_dec_red, *fired_red, *part_accum;     /* [F], [d], [F], [1] */
+  float *gb_enc_red, *gb_dec_red, *fired_red, *part_accum;     /* [F], [d], [F], [4] */
   float* b_dec; void* scalars;
   float *m_dec, *v_dec, *m_enc, *v_enc, *m_be, *v_be, *m_bd, *v_bd;   /* only the owned row slice is touched */
   float* since_fired; float* act_freq;
@@ -389,6 +389,9 @@ PB_API int pb_p2p_barrier(const PbP2PStep* s, uint32_t epoch, pb_stream_t stream
 PB_API int pb_p2p_sum_xsum(const PbP2PStep* s, float* xsum_global, pb_stream_t stream);
 PB_API int pb_p2p_reduce_scatter(const PbP2PStep* s, pb_stream_t stream);
 PB_API int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream);
+/* after the barrier that follows pb_p2p_adam_allgather: enc_norm_max[0..1] (PbSaeEncode.enc_norm_max) = max over ranks of the
+ * encoder row-norm maxima each rank measured on its owned rows; norm_parts must hold 3 * PB_P2P_MAX_RANKS floats, part_accum 4 */
+PB_API int pb_p2p_wmax(const PbP2PStep* s, float* enc_norm_max, pb_stream_t stream);
 /* NVSwitch multicast memory (csrc/mc.cu).  Collective protocol, driven from the host side (vit_prisma/b200/p2p.py):
  *   every rank pb_mc_supported -> rank 0 pb_mc_create (fd) -> fd to the other ranks (SCM_RIGHTS) -> pb_mc_import ->
  *   every rank pb_mc_add_device -> barrier -> every rank pb_mc_bind_alloc -> barrier.  PB_EUNSUPPORTED = fall back.      */

@@ -692,15 +692,22 @@ int pb_gemm_tc(const PbGemm* g, cudaStream_t st) {
   }
   static int variant = -1;  // PB_GEMM_TC_VARIANT=1 forces the one-tile-per-CTA kernel (A/B measurements)
   if (variant < 0) { const char* e = getenv("PB_GEMM_TC_VARIANT"); variant = e ? atoi(e) : 0; }
+  // CTA pairs (cta_group::2, 256 x 256 per pair, gemm_tc_pair.cuh): each SM loads half of the B tile, which is what the persistent
+  // single-CTA kernel was waiting for.  Measured on the ViT-B/32 shapes at M = 25600 (profiles/r02_gemm_notes.md):
+  //   3xTF32  +6 .. +18 % on every shape and epilogue   -> default whenever M, N >= 256
+  //   bf16    +1 .. +9 % with one output / a residual epilogue, -5 % with the two-output GELU epilogue (epilogue-bound: the pair
+  //           couples two epilogues to one accumulator hand-back)  -> default except for activation epilogues
+  // PB_GEMM_TC_VARIANT: 0 = this policy, 1 = one tile per CTA (v1), 2 = fp32 wide single-CTA tile, 3 = pairs everywhere, 4 = never pairs.
+  const bool pair_ok = g->N >= 256 && g->M >= 256 && variant != 1 && variant != 2 && variant != 4;
   if (g->dtype == PB_BF16) {
-    // variant 3: CTA pairs (cta_group::2), 256 x 256 per pair -- opt-in until it has been measured against variant 0 on every shape
-    if (variant == 3 && g->N >= 256 && g->M >= 256) return launch_tc2_pair<bf16, 1, 256, 6, 8>(g, st);
+    const bool act_epilogue = g->out1 && !g->residual && g->act != PB_ACT_NONE;
+    if (pair_ok && (variant == 3 || !act_epilogue)) return launch_tc2_pair<bf16, 1, 256, 6, 8>(g, st);
     if (variant != 1 && g->N >= 256) return launch_tc2<bf16, 1, 256, 4, 8>(g, st);
     if (variant != 1 && g->N >= 128) return launch_tc2<bf16, 1, 128, 4, 4>(g, st);
     return launch_tc<bf16, 1, 128, 3>(g, st);
   }
   if (variant == 2 && g->N >= 256) return launch_tc2<float, 3, 256, 2, 4>(g, st);   // wider tile, shallower ring (A/B)
-  if (variant == 3 && g->N >= 256 && g->M >= 256) return launch_tc2_pair<float, 3, 256, 3, 4>(g, st);
+  if (pair_ok) return launch_tc2_pair<float, 3, 256, 3, 4>(g, st);
   if (variant != 1) return launch_tc2<float, 3, 128, 3, 4>(g, st);
   return launch_tc<float, 3, 128, 3>(g, st);
 }

@@ -31,10 +31,10 @@ __device__ __forceinline__ float4 mc_ld_reduce4(const float* mc_addr) {
   return v;
 }
 __device__ __forceinline__ void mc_st4(float* mc_addr, const float (&v)[4]) {
-  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+  asm volatile("multimem.st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");   // weak: the flag barrier's system fence publishes it
 }
 __device__ __forceinline__ void mc_st1(float* mc_addr, float v) {
-  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+  asm volatile("multimem.st.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
 }
 
 struct P2PTables {
@@ -123,20 +123,35 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PTables t, int f0,
   const int64_t n4 = (int64_t)(f1 - f0) * d / 4;
   const int64_t base4 = (int64_t)f0 * d / 4;
   float nsq = 0.f;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   for (int m = 0; m < 2; ++m) {
     float4* own = reinterpret_cast<float4*>(m == 0 ? t.gW_dec[t.rank] : t.gW_encT[t.rank]) + base4;
     const float* mc = m == 0 ? mc_gW_dec : mc_gW_encT;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-      float4 acc;
-      if (mc) {
-        acc = mc_ld_reduce4(mc + 4 * (base4 + i));          // summed inside the switch: this slice crosses NVLink once
-      } else {
-        acc = own[i];
-        for (int r = 0; r < t.world; ++r) {
-          if (r == t.rank) continue;
-          const float4 v = (reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4)[i];   // peer load (NVLink)
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+    if (mc) {
+      // summed inside the switch: this slice crosses NVLink once.  A multimem load is a round trip through the switch (several
+      // microseconds): four independent loads per thread keep enough bytes in flight (one per trip ran at 270 GB/s, r2d_bench2).
+      const float* src = mc + 4 * base4;
+      int64_t i = tid;
+      for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a0 = mc_ld_reduce4(src + 4 * i), a1 = mc_ld_reduce4(src + 4 * (i + stride)), a2 = mc_ld_reduce4(src + 4 * (i + 2 * stride)),
+                     a3 = mc_ld_reduce4(src + 4 * (i + 3 * stride));
+        own[i] = a0; own[i + stride] = a1; own[i + 2 * stride] = a2; own[i + 3 * stride] = a3;
+        nsq += a0.x * a0.x + a0.y * a0.y + a0.z * a0.z + a0.w * a0.w + a1.x * a1.x + a1.y * a1.y + a1.z * a1.z + a1.w * a1.w +
+               a2.x * a2.x + a2.y * a2.y + a2.z * a2.z + a2.w * a2.w + a3.x * a3.x + a3.y * a3.y + a3.z * a3.z + a3.w * a3.w;
+      }
+      for (; i < n4; i += stride) {
+        const float4 a = mc_ld_reduce4(src + 4 * i);
+        own[i] = a;
+        nsq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+      }
+      continue;
+    }
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 acc = own[i];
+      for (int r = 0; r < t.world; ++r) {
+        if (r == t.rank) continue;
+        const float4 v = (reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4)[i];   // peer load (NVLink)
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
       own[i] = acc;
       nsq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
@@ -193,8 +208,9 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
                                                            float* __restrict__ m_dec, float* __restrict__ v_dec, float* __restrict__ m_enc,
                                                            float* __restrict__ v_enc, float* __restrict__ m_be, float* __restrict__ v_be,
                                                            const SaeScalarsP2P* __restrict__ sc, AdamHyperP2P h, float* __restrict__ mc_W_dec,
-                                                           float* __restrict__ mc_W_encT, float* __restrict__ mc_b_enc) {
+                                                           float* __restrict__ mc_W_encT, float* __restrict__ mc_b_enc, float* __restrict__ wmax_accum) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float enc_best = 0.f, enc_best_lo = 0.f;
   const int nvec = d >> 2;
   const float clip = sc->clip_coef;
   float* W_dec = t.W_dec[t.rank];
@@ -246,6 +262,7 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
         else for (int r = 0; r < t.world; ++r) st4(t.W_dec[r] + base + 4 * c4, w[i]);      // all-gather: peer stores
       }
     }
+    float esq = 0.f, elo = 0.f;
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
       const int c4 = i * 32 + lane;
@@ -259,6 +276,9 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
         for (int q = 0; q < 4; ++q) {
           p[q] = adam_upd(p[q], gr[q] * clip, mm[q], vv[q], h);
           lo[q] = tf32_lo(p[q]);
+          esq = fmaf(p[q], p[q], esq);
+          const float tl = p[q] - tf32_trunc(p[q]);
+          elo = fmaf(tl, tl, elo);
         }
         st4(m_enc + base + 4 * c4, mm);
         st4(v_enc + base + 4 * c4, vv);
@@ -272,6 +292,8 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
         }
       }
     }
+    enc_best = fmaxf(enc_best, warp_sum(esq));
+    enc_best_lo = fmaxf(enc_best_lo, warp_sum(elo));
     if (lane == 0) {
       float mm = m_be[f], vv = v_be[f];
       const float nb = adam_upd(t.b_enc[t.rank][f], gb_enc_red[f] * clip, mm, vv, h);
@@ -281,6 +303,29 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
       else for (int r = 0; r < t.world; ++r) t.b_enc[r][f] = nb;
     }
   }
+  // largest encoder-column norms of the OWNED rows (error bound of the fused encoder's tf32 pass); merged across ranks by pb_p2p_wmax
+  if (wmax_accum && lane == 0 && enc_best > 0.f) {
+    atomicMax(reinterpret_cast<unsigned int*>(wmax_accum), __float_as_uint(sqrtf(enc_best)));
+    atomicMax(reinterpret_cast<unsigned int*>(wmax_accum) + 1, __float_as_uint(sqrtf(enc_best_lo)));
+  }
+}
+
+// norm_parts layout on every rank: [0, 8) gradient-norm partials, [8, 16) max ||w_f|| partials, [16, 24) max ||w_f - trunc(w_f)|| partials
+__global__ void k_p2p_publish_wmax(P2PTables t, const float* __restrict__ wmax_accum) {
+  const int r = threadIdx.x;
+  if (r < t.world) {
+    t.norm_parts[r][PB_MAX_RANKS + t.rank] = wmax_accum[0];          // peer stores
+    t.norm_parts[r][2 * PB_MAX_RANKS + t.rank] = wmax_accum[1];
+  }
+}
+__global__ void k_p2p_wmax_reduce(P2PTables t, float* __restrict__ enc_norm_max) {
+  float a = 0.f, b = 0.f;
+  for (int r = 0; r < t.world; ++r) {
+    a = fmaxf(a, t.norm_parts[t.rank][PB_MAX_RANKS + r]);
+    b = fmaxf(b, t.norm_parts[t.rank][2 * PB_MAX_RANKS + r]);
+  }
+  enc_norm_max[0] = a;
+  enc_norm_max[1] = b;
 }
 
 // replicated tiny updates: b_dec Adam (identical inputs on every rank -> identical result) and the dead-feature counters
@@ -344,7 +389,7 @@ extern "C" int pb_p2p_reduce_scatter(const PbP2PStep* s, pb_stream_t stream) {
   PB_LAUNCH_CHECK();
   k_p2p_sum_small<<<(s->F + 255) / 256, 256, 0, st>>>(t, s->fired_red, 3, s->F);
   PB_LAUNCH_CHECK();
-  PB_CUDA(cudaMemsetAsync(s->part_accum, 0, sizeof(float), st));
+  PB_CUDA(cudaMemsetAsync(s->part_accum, 0, 4 * sizeof(float), st));   // [0] gradient-norm partial, [1..2] encoder row-norm maxima of the owned slice
   PB_CHECK_ARG(!s->mc_gW_dec == !s->mc_gW_encT, "pb_p2p_reduce_scatter: both multicast gradient views or none");
   k_p2p_reduce_scatter<<<pb_sm_count() * 4, 256, 0, st>>>(t, f0, f1, s->d, s->gb_enc_red, s->gb_dec_red, s->F, s->part_accum, s->mc_gW_dec,
                                                           s->mc_gW_encT);
@@ -373,7 +418,7 @@ extern "C" int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream) {
   int grid = pb_sm_count() * 4;
   if (grid > (per + 7) / 8) grid = (per + 7) / 8;
   PB_CHECK_ARG((!s->mc_W_dec == !s->mc_W_encT) && (!s->mc_W_dec == !s->mc_b_enc), "pb_p2p_adam_allgather: all three multicast parameter views or none");
-#define PB_P2P_ADAM(CH) k_p2p_adam_allgather<CH><<<grid, 256, 0, st>>>(t, f0, f1, d, s->gb_enc_red, s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, (const SaeScalarsP2P*)s->scalars, h, s->mc_W_dec, s->mc_W_encT, s->mc_b_enc)
+#define PB_P2P_ADAM(CH) k_p2p_adam_allgather<CH><<<grid, 256, 0, st>>>(t, f0, f1, d, s->gb_enc_red, s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, (const SaeScalarsP2P*)s->scalars, h, s->mc_W_dec, s->mc_W_encT, s->mc_b_enc, s->part_accum + 1)
   const int nvec = d / 4;
   if (d % 4 != 0 || nvec > 384) { pb_set_error("pb_p2p_adam_allgather: d_in=%d unsupported", d); return PB_EUNSUPPORTED; }
   if (nvec <= 32) PB_P2P_ADAM(1);
@@ -384,8 +429,20 @@ extern "C" int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream) {
   else PB_P2P_ADAM(12);
 #undef PB_P2P_ADAM
   PB_LAUNCH_CHECK();
+  k_p2p_publish_wmax<<<1, 32, 0, st>>>(t, s->part_accum + 1);
+  PB_LAUNCH_CHECK();
   k_p2p_small_updates<<<(s->F + 255) / 256, 256, 0, st>>>(s->b_dec, s->gb_dec_red, s->m_bd, s->v_bd, s->fired_red, s->since_fired, s->act_freq,
                                                         (const SaeScalarsP2P*)s->scalars, h, d, s->F);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// after the barrier that follows pb_p2p_adam_allgather: enc_norm_max[0..1] = max over ranks of the published row-norm maxima
+extern "C" int pb_p2p_wmax(const PbP2PStep* s, float* enc_norm_max, pb_stream_t stream) {
+  P2PTables t;
+  PB_TRY(fill_tables(s, &t));
+  PB_CHECK_ARG(enc_norm_max, "pb_p2p_wmax: output missing");
+  k_p2p_wmax_reduce<<<1, 1, 0, (cudaStream_t)stream>>>(t, enc_norm_max);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

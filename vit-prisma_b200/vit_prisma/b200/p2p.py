@@ -44,6 +44,7 @@ L.register_signatures({
     "pb_p2p_sum_xsum": (i32, [C.POINTER(PbP2PStep), vp, vp]),
     "pb_p2p_reduce_scatter": (i32, [C.POINTER(PbP2PStep), vp]),
     "pb_p2p_adam_allgather": (i32, [C.POINTER(PbP2PStep), vp]),
+    "pb_p2p_wmax": (i32, [C.POINTER(PbP2PStep), vp, vp]),
     "pb_mc_supported": (i32, [C.POINTER(i32)]),
     "pb_mc_round_size": (i32, [i32, i64, C.POINTER(i64)]),
     "pb_mc_create": (i32, [i32, i64, C.POINTER(u64), C.POINTER(i32)]),
@@ -242,7 +243,7 @@ class SaeDPEngine(SaeStepEngine):
         shared["W_encT"].copy_(W_encT)
         shared["W_dec"].copy_(W_dec)
         shared["b_enc"].copy_(b_enc)
-        for name, shape in (("gb_enc", (F,)), ("gb_dec", (d,)), ("fired", (F,)), ("xsum", (d,)), ("norm_parts", (MAX_RANKS,))):
+        for name, shape in (("gb_enc", (F,)), ("gb_dec", (d,)), ("fired", (F,)), ("xsum", (d,)), ("norm_parts", (3 * MAX_RANKS,))):
             g.alloc(name, shape)
         g.alloc("flags", (MAX_RANKS,), dtype=torch.int32)
         super().__init__(shared["W_encT"], shared["W_dec"], shared["b_enc"], b_dec.clone().contiguous(), k, **kw)
@@ -255,7 +256,7 @@ class SaeDPEngine(SaeStepEngine):
         self.xsum_local = g.local["xsum"]
         dev = W_dec.device
         self.gb_enc_red, self.gb_dec_red, self.fired_red = torch.zeros(F, device=dev), torch.zeros(d, device=dev), torch.zeros(F, device=dev)
-        self.part_accum = torch.zeros(1, device=dev)
+        self.part_accum = torch.zeros(4, device=dev)        # gradient-norm partial + encoder row-norm maxima of the owned slice
         g.connect()
         torch.cuda.synchronize()
 
@@ -293,16 +294,17 @@ class SaeDPEngine(SaeStepEngine):
                                     "drop or pad short batches before the data-parallel step")
         self._dp_rows = rows
         # prep writes THIS rank's column sums of x into the shared xsum; decode needs the GLOBAL sums
-        xsum_global, self.xsum = self.xsum, self.xsum_local
-        self.encode_topk(x)
-        self.xsum = xsum_global
-        self.scalars.zero_()
+        self._ensure_rows(rows)
         self.step_count += 1
+        s = self._desc(x, training=True, lr=float(lr), since_fired=since_fired, act_freq=act_freq, want_out=want_out)
+        s.global_rows, s.dist, s.pre_zeroed = rows * g.world, 1, 1
+        L.check(lib.pb_sae_step_reset(C.byref(s), self.fb_count.data_ptr(), st), "pb_sae_step_reset")     # every accumulator of the step, one launch
+        xsum_global, self.xsum = self.xsum, self.xsum_local
+        self.encode_topk(x, pre_zeroed=True)
+        self.xsum = xsum_global
         ps = self._p2p_desc(rows, float(lr), since_fired, act_freq)
         g.barrier(ps)
         L.check(lib.pb_p2p_sum_xsum(C.byref(ps), self.xsum.data_ptr(), st), "pb_p2p_sum_xsum")
-        s = self._desc(x, training=True, lr=float(lr), since_fired=since_fired, act_freq=act_freq, want_out=want_out)
-        s.global_rows, s.dist = rows * g.world, 1
         L.check(lib.pb_sae_decode(C.byref(s), st), "pb_sae_decode")
         L.check(lib.pb_sae_backward(C.byref(s), st), "pb_sae_backward")
         g.barrier(ps)                                   # every rank's local gradients are complete
@@ -310,8 +312,8 @@ class SaeDPEngine(SaeStepEngine):
         g.barrier(ps)                                   # norm partials published; all peer reads of this step are done
         L.check(lib.pb_p2p_adam_allgather(C.byref(ps), st), "pb_p2p_adam_allgather")
         g.barrier(ps)                                   # every rank holds the updated parameters
-        if self.encoder == "fused":                     # error bound of the next step's tf32 pass: largest encoder-column norm
-            L.check(lib.pb_rownorm_max(self.W_encT.data_ptr(), self.F, self.d, self.enc_norm_max.data_ptr(), st), "pb_rownorm_max")
+        if self.encoder == "fused":                     # error bound of the next step's tf32 pass: largest encoder-column norms, merged over ranks
+            L.check(lib.pb_p2p_wmax(C.byref(ps), self.enc_norm_max.data_ptr(), st), "pb_p2p_wmax")
         return self.scalars
 
     # ------------------------------------------------------------------ instrumentation: COLLECTIVE (every rank must call it)
