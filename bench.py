@@ -652,6 +652,74 @@ def run_sae(args, ctx):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def run_cfg4(args, ctx):
+    """BASELINE.json configs[3]: CLIP ViT-L/14 run_with_cache feeding an SAE (d_model 1024, dict 1024 x 64, TopK 32), data parallel:
+    every rank runs its own VisionActivationsStore over its own synthetic image shard (names_filter = one resid_post,
+    stop_at_layer = layer + 1, exactly the store's call) and trains on its own token shard through VisionSAETrainer.train_step;
+    the SAE step is the NVLink data-parallel step.  A "step" = one train_step on 4096 tokens per GPU INCLUDING the store refills
+    it triggers (the ViT forward dominates: 257 tokens per image)."""
+    from torch.utils.data import TensorDataset
+    from vit_prisma.b200.synthetic import CLIP_L14
+    from vit_prisma.sae.training.activations_store import VisionActivationsStore
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    vit_dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    model = build_model(vit_dtype, dev, CLIP_L14)
+    d, expansion, k, Bt, layer = 1024, 64, 32, 4096, args.layer
+    cfg = sae_runner_cfg(d, expansion, k, Bt, hook_point_layer=layer, layer_subtype="hook_resid_post", context_size=257, store_batch_size=32,
+                         n_batches_in_buffer=8, image_size=224, num_workers=0)
+    g = torch.Generator().manual_seed(100 + rank)
+    images = torch.randn(256, 3, 224, 224, generator=g).to(vit_dtype)
+    with contextlib.redirect_stdout(io.StringIO()):
+        store = VisionActivationsStore(cfg, model, TensorDataset(images, torch.zeros(256, dtype=torch.long)), num_workers=0)
+    group = None
+    if world > 1:
+        from vit_prisma.b200.p2p import P2PGroup
+        group = P2PGroup(rank, world, dev)
+    trainer = build_sae_trainer(ctx, cfg, store, group)
+    sae = trainer.sparse_coder
+    act_freq, since_fired, n_frac, optimizer, scheduler = trainer.initialize_training_variables()
+    trainer.initialize_geometric_medians()
+    trainer.enable_data_parallel_if_requested()
+    eng = sae.step_engine()
+    state = {"step": 0, "n_frac": n_frac}
+
+    def step():
+        batch = store.next_batch()
+        while batch.shape[0] != Bt:                       # the tail of a served half-buffer: skip (DP needs equal row counts)
+            batch = store.next_batch()
+        out = trainer.train_step(sparse_autoencoder=sae, optimizer=optimizer, scheduler=scheduler, act_freq_scores=act_freq,
+                                 n_forward_passes_since_fired=since_fired, n_frac_active_tokens=state["n_frac"], layer_acts=batch.float(),
+                                 n_training_steps=state["step"], n_training_tokens=state["step"] * Bt * world)
+        state["step"] += 1
+        state["n_frac"] = out[-1]
+        return out[0]
+
+    for _ in range(args.warmup):
+        step()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    if rank != 0:
+        return None
+    tokens = world * Bt * args.steps
+    return {"metric": "SAE training tokens/sec fed by CLIP ViT-L/14 run_with_cache (cfg #4: d_model 1024, dict 1024x64, k=32)",
+            "value": tokens / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": f"vit {args.dtype} / sae fp32", "data": "synthetic",
+            "config": {"workload": "cfg4_vit_l14_store_feeding_sae", "api": "VisionActivationsStore.next_batch + VisionSAETrainer.train_step",
+                       "hook_point": cfg.hook_point, "d_in": d, "d_sae": d * expansion, "k": k, "tokens_per_step_per_gpu": Bt,
+                       "store_batch_size": 32, "n_batches_in_buffer": 8, "images_per_rank": 256, "engine": type(eng).__name__,
+                       "encoder": eng.describe_encoder(),
+                       "parallelism": f"dp{world}" + (" (" + eng.describe_exchange() + ")" if world > 1 else "")},
+            "final_loss": float(loss)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def dp_parity_gate(ctx):
     """N > 1 only, after the timed regions: the NVLink data-parallel step, driven through VisionSAETrainer(p2p_group=...), must
     reproduce the reference's single-process training of tests/golden/sae_tiny_b.pt (fixture made by the unmodified reference):
@@ -738,7 +806,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "sae", "vit"],
+    ap.add_argument("--workload", default="all", choices=["all", "sae", "vit", "cfg4"],
                     help="all (default) = SAE training step as the headline record + the full run_with_cache record under 'secondary'")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="ViT model dtype (the SAE step is fp32)")
     ap.add_argument("--batch", type=int, default=512, help="ViT images per step per GPU")
@@ -754,6 +822,8 @@ def main():
     rc = 0
     try:
         line = None
+        if args.workload == "cfg4":
+            line = run_cfg4(args, ctx)
         if args.workload in ("all", "sae"):
             line = run_sae(args, ctx)
             if ctx.world > 1:

@@ -82,7 +82,8 @@ def test_substitution_loss_matches_the_spliced_model_and_the_oracle_clean_loss()
     sae.set_decoder_norm_to_unit_norm()
     x = torch.randn(6, 3, 32, 32)
     labels = torch.tensor([1, 4, 0, 9, 3, 3])
-    text = torch.nn.functional.normalize(torch.randn(10, VIT["n_classes"]), dim=-1)
+    out_dim = model(x.cuda()).shape[-1]                                    # the embedding the text features are compared with
+    text = torch.nn.functional.normalize(torch.randn(10, out_dim), dim=-1)
     score, loss, recons, zero = get_substitution_loss(sae, model, x, labels, text, device=torch.device("cuda"))
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     cfg = dict(VIT, n_channels=3, eps=model.cfg.eps, activation_name=model.cfg.activation_name, normalization_type=model.cfg.normalization_type,

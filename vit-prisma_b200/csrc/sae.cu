@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) k_csc_fill(const int* __restrict__ idx, i
 //    fired[f]   = number of tokens with relu(val) > 0 ; gnorm_sq += all squares
 // Entry order inside a feature list comes from atomics, so the fp32 sums are order-nondeterministic at the
 // 1e-7 level; the list is therefore sorted by token index first (lists are short: mean Bt*k/F).
-constexpr int SAE_LONG_LIST = 64;    // lists longer than this are split across warps
+constexpr int SAE_LONG_LIST = 32;    // lists longer than a warp are split into chunks across warps (k_sae_grads_long)
 constexpr int SAE_LONG_CHUNK = 32;   // entries per work item of the long-list kernel
 struct SaeWorkHeader { int n_chunks, n_long, next_f, pad; };   // followed in memory by work_feats[F] and work_chunks[2 * capacity]
 constexpr int SAE_CLAIM = 4;         // features a warp claims per trip to the dynamic queue
@@ -464,62 +464,38 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
       }
       continue;
     }
-    if (len > 1 && len <= 32) {
-      // rank-by-counting in registers: lane i holds entry i, its sorted slot = number of smaller entries (entries are distinct).
-      // (A serial insertion sort through global memory here cost 3.6 ms per step: profiles/r01_sae_notes.md.)
+    // The whole list (<= 32 entries) lives in the warp: lane i loads entry i, its sorted slot is the number of smaller entries
+    // (rank by counting: entries are distinct; token order makes the fp32 sums deterministic), then lane i loads ITS entry's
+    // activation / d(pre-activation) / token row index.  The accumulation loop below only shuffles those out of registers, so the
+    // row gathers of consecutive entries are independent loads in flight together.  (Before: entry -> val / dval -> rows was a chain
+    // of three dependent L2 round trips PER PAIR of entries, ~8 us per feature: profiles/r02_sae_notes.md.)
+    int my_b = 0;
+    float my_a = 0.f, my_dp = 0.f;
+    {
       const int mine = lane < len ? entries[e0 + lane] : 0x7fffffff;
       int rank = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) rank += __shfl_sync(0xffffffffu, mine, j) < mine ? 1 : 0;
-      __syncwarp();
-      if (lane < len) entries[e0 + rank] = mine;
-      __syncwarp();
+      // lane `rank` must hold `mine`: invert the permutation with one shuffle per lane (lane j looks for the lane whose rank is j)
+      int src = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) src = (__shfl_sync(0xffffffffu, rank, j) == lane && j < len) ? j : src;
+      const int sorted = __shfl_sync(0xffffffffu, mine, src);
+      if (lane < len) {
+        my_b = sorted / k;
+        my_a = fmaxf(val[sorted], 0.f);
+        my_dp = dval[sorted];
+      }
     }
     float ad[CHUNKS][4], ae[CHUNKS][4];
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) ad[i][0] = ad[i][1] = ad[i][2] = ad[i][3] = ae[i][0] = ae[i][1] = ae[i][2] = ae[i][3] = 0.f;
-    float gbe = 0.f, npos = 0.f;
-    // two list entries per trip: the row gathers of both are in flight together (the walk is a chain of dependent L2 loads --
-    // entry -> token -> rows of g / sae_in -- latency-bound at ~20 % of the warp slots, profiles/r01_sae_step_ncu_summary.txt).
-    // Entries are accumulated in list order, so the sums are bit-identical to the one-at-a-time walk.  Measured: no change of the
-    // backward stage on the synthetic bench (0.32 -> 0.34 ms, noise): the stage is bounded by the hot-feature queue and the CTA
-    // tail, not by this loop; a dynamic (atomic) feature queue is the next thing to try.
-    int p = e0;
-    for (; p + 1 < e1; p += 2) {
-      const int ea = entries[p], eb = entries[p + 1];
-      const int ba = ea / k, bb = eb / k;
-      const float aa = fmaxf(val[ea], 0.f), ab = fmaxf(val[eb], 0.f);
-      const float dpa = dval[ea], dpb = dval[eb];
-      npos += (aa > 0.f ? 1.f : 0.f) + (ab > 0.f ? 1.f : 0.f);
-      gbe += dpa;
-      gbe += dpb;
-      const float* gra = g + (int64_t)ba * d;
-      const float* sra = sae_in + (int64_t)ba * d;
-      const float* grb = g + (int64_t)bb * d;
-      const float* srb = sae_in + (int64_t)bb * d;
-#pragma unroll
-      for (int i = 0; i < CHUNKS; ++i) {
-        const int c4 = i * 32 + lane;
-        if (c4 < nvec) {
-          float gva[4], sva[4], gvb[4], svb[4];
-          ld4(gra + 4 * c4, gva);
-          ld4(sra + 4 * c4, sva);
-          ld4(grb + 4 * c4, gvb);
-          ld4(srb + 4 * c4, svb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            ad[i][q] = fmaf(ab, gvb[q], fmaf(aa, gva[q], ad[i][q]));
-            ae[i][q] = fmaf(dpb, svb[q], fmaf(dpa, sva[q], ae[i][q]));
-          }
-        }
-      }
-    }
-    if (p < e1) {
-      const int e = entries[p];
-      const int b = e / k;
-      const float a = fmaxf(val[e], 0.f);
-      const float dp = dval[e];
-      if (a > 0.f) npos += 1.f;
+    float gbe = 0.f;
+    const float npos = (float)__popc(__ballot_sync(0xffffffffu, my_a > 0.f));
+#pragma unroll 2
+    for (int j = 0; j < len; ++j) {
+      const float a = __shfl_sync(0xffffffffu, my_a, j), dp = __shfl_sync(0xffffffffu, my_dp, j);
+      const int b = __shfl_sync(0xffffffffu, my_b, j);
       gbe += dp;
       const float* gr = g + (int64_t)b * d;
       const float* sr = sae_in + (int64_t)b * d;
@@ -607,13 +583,21 @@ __global__ void __launch_bounds__(256) k_sae_grads_long(const int* __restrict__ 
     float ad[CHUNKS][4], ae[CHUNKS][4];
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) ad[i][0] = ad[i][1] = ad[i][2] = ad[i][3] = ae[i][0] = ae[i][1] = ae[i][2] = ae[i][3] = 0.f;
-    float gbe = 0.f, npos = 0.f;
-    for (int p = p0; p < p1; ++p) {
-      const int e = entries[p];
-      const int b = e / k;
-      const float a = fmaxf(val[e], 0.f);
-      const float dp = dval[e];
-      if (a > 0.f) npos += 1.f;
+    const int n = p1 - p0;                                   // <= SAE_LONG_CHUNK = 32: one entry per lane
+    int my_b = 0;
+    float my_a = 0.f, my_dp = 0.f;
+    if (lane < n) {
+      const int e = entries[p0 + lane];
+      my_b = e / k;
+      my_a = fmaxf(val[e], 0.f);
+      my_dp = dval[e];
+    }
+    float gbe = 0.f;
+    const float npos = (float)__popc(__ballot_sync(0xffffffffu, my_a > 0.f));
+#pragma unroll 2
+    for (int j = 0; j < n; ++j) {
+      const float a = __shfl_sync(0xffffffffu, my_a, j), dp = __shfl_sync(0xffffffffu, my_dp, j);
+      const int b = __shfl_sync(0xffffffffu, my_b, j);
       gbe += dp;
       const float* gr = g + (int64_t)b * d;
       const float* sr = sae_in + (int64_t)b * d;
