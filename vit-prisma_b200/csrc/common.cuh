@@ -130,3 +130,40 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------- programmatic dependent launch (PDL)
+// The SAE training step is ~15 short dependent kernels; launched back to back they leave the GPU idle for a few microseconds at
+// every boundary (grid launch latency + block ramp-up).  With the programmatic-stream-serialization attribute the NEXT kernel's
+// blocks are dispatched as soon as every block of the current kernel has executed `griddepcontrol.launch_dependents` (first thing
+// each kernel does) and then park in `griddepcontrol.wait` until the current kernel has completed and flushed -- so correctness
+// is exactly stream order, only the dispatch latency is hidden.  PB_PDL=0 in the environment launches plainly (A/B, debugging).
+__device__ __forceinline__ void pb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pb_pdl() { pb_pdl_trigger(); pb_pdl_wait(); }
+
+bool pb_pdl_enabled();   // library.cu-level switch (PB_PDL environment variable, default on)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define PB_LAUNCH_PDL(kern, grid, block, smem, st, ...)                                  \
+  do {                                                                                   \
+    cudaError_t le__ = pb_launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__); \
+    ++g_pb_launches;                                                                     \
+    if (le__ != cudaSuccess) {                                                           \
+      pb_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(le__)); \
+      return PB_ECUDA;                                                                   \
+    }                                                                                    \
+  } while (0)

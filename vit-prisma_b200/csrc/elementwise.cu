@@ -4,6 +4,7 @@
 // the rule is 16-byte vector accesses, grid sized to a multiple of the SM count, grid-stride
 // loops.  Reference call sites are cited at each entry point.
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 
 // ------------------------------------------------------------------ library
@@ -18,6 +19,12 @@ extern "C" const char* pb_last_error(void) { return g_err; }
 extern "C" int pb_version(void) { return 100; }
 unsigned long long g_pb_launches = 0;
 extern "C" unsigned long long pb_launch_count(void) { return g_pb_launches; }
+
+bool pb_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("PB_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
 
 int pb_sm_count() {
   static int cached[64] = {0};

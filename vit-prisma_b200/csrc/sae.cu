@@ -40,6 +40,7 @@ template <int CHUNKS>
 __global__ void __launch_bounds__(256) k_sae_prep(const float* __restrict__ x, const float* __restrict__ b_dec, float* __restrict__ sae_in,
                                                   float* __restrict__ sae_in_lo, float* __restrict__ mu_out, float* __restrict__ std_out,
                                                   int rows, int d, int norm_mode, float eps) {
+  pb_pdl();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) k_sae_prep(const float* __restrict__ x, c
 
 // column sums: out[c] += sum_r x[r,c]   (rows split across CTAs, one atomic per column per CTA)
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ x, float* __restrict__ out, int rows, int d, int rows_per_cta) {
+  pb_pdl();
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float acc = 0.f;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(256) k_sae_decode(const float* __restrict__ x,
                                                     float* __restrict__ sae_out, float* __restrict__ g_out, float* __restrict__ dval,
                                                     SaeScalars* __restrict__ sc, int rows, int d, int k, int norm_mode, int training,
                                                     float inv_rows) {
+  pb_pdl();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const bool active = row < rows;
@@ -341,53 +344,67 @@ __global__ void __launch_bounds__(256) k_sae_decode(const float* __restrict__ x,
 
 // ---------------------------------------------------------------------------------------------
 // 4. CSC build: feat_count (float, from k_topk) -> offsets (exclusive scan) ; fill entries
-// One CTA of 1024 threads.  Batches of 16 chunks of 1024 counts: the 16 coalesced loads of a batch are issued together (one memory
-// latency), then each chunk is block-scanned (warp shuffles + one shared array of warp totals) on top of the running total.
-// (The first version gave every thread a contiguous run of F / 1024 counts: 2 x 24 dependent uncoalesced loads = 35 us of latency.)
+// One CTA of 1024 threads; thread t owns the contiguous run [t * per, (t + 1) * per) of the counts (per = ceil(F / 1024) rounded up to
+// a multiple of 4): 16-byte loads, a register prefix inside the run, ONE block scan of the 1024 run totals, 16-byte stores.
+// (v1 walked its run with dependent scalar loads: 35 us; v2 block-scanned 1024-count chunks: 96 barriers, 15 us.)
+template <int PER>
 __global__ void __launch_bounds__(1024) k_scan_counts(const float* __restrict__ cnt, int* __restrict__ off, int* __restrict__ cursor, int F) {
+  pb_pdl();
   __shared__ int wtot[32];
-  __shared__ int carry_s;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  int carry = 0;
-  for (int base = 0; base < F; base += 16 * 1024) {
-    int v[16];
+  const int base = t * PER;
+  int v[PER];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int p = base + i * 1024 + t;
-      v[i] = p < F ? (int)cnt[p] : 0;
+  for (int i = 0; i < PER; i += 4) {
+    const int p = base + i;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p + 3 < F) c = *reinterpret_cast<const float4*>(cnt + p);
+    else {
+      if (p < F) c.x = cnt[p];
+      if (p + 1 < F) c.y = cnt[p + 1];
+      if (p + 2 < F) c.z = cnt[p + 2];
     }
+    v[i] = (int)c.x; v[i + 1] = (int)c.y; v[i + 2] = (int)c.z; v[i + 3] = (int)c.w;
+  }
+  int run = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (base + i * 1024 >= F) break;
-      int x = v[i];                                  // inclusive scan inside the warp
+  for (int i = 0; i < PER; ++i) { const int x = v[i]; v[i] = run; run += x; }       // exclusive prefix inside the run
+  int x = run;                                                                         // inclusive scan of the run totals
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      if (lane == 31) wtot[warp] = x;
-      __syncthreads();
-      if (warp == 0) {
-        int w = wtot[lane];
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wtot[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wtot[lane];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(0xffffffffu, w, o);
-          if (lane >= o) w += y;
-        }
-        wtot[lane] = w;                              // inclusive totals of warps 0..lane
-        if (lane == 31) carry_s = w;
-      }
-      __syncthreads();
-      const int excl = carry + (warp ? wtot[warp - 1] : 0) + x - v[i];
-      const int p = base + i * 1024 + t;
-      if (p < F) { off[p] = excl; cursor[p] = excl; }
-      carry += carry_s;
-      __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    wtot[lane] = w;
+  }
+  __syncthreads();
+  const int excl = (warp ? wtot[warp - 1] : 0) + x - run;
+#pragma unroll
+  for (int i = 0; i < PER; i += 4) {
+    const int p = base + i;
+    const int4 o4 = make_int4(excl + v[i], excl + v[i + 1], excl + v[i + 2], excl + v[i + 3]);
+    if (p + 3 < F) {
+      *reinterpret_cast<int4*>(off + p) = o4;
+      *reinterpret_cast<int4*>(cursor + p) = o4;
+    } else {
+      const int o[4] = {o4.x, o4.y, o4.z, o4.w};
+      for (int j = 0; j < 4; ++j)
+        if (p + j < F) { off[p + j] = o[j]; cursor[p + j] = o[j]; }
     }
   }
-  if (t == 0) off[F] = carry;
+  if (t == 1023) off[F] = wtot[31];
 }
 __global__ void __launch_bounds__(256) k_csc_fill(const int* __restrict__ idx, int* __restrict__ cursor, int* __restrict__ entries, int64_t n) {
+  pb_pdl();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int f = idx[e];
     const int pos = atomicAdd(cursor + f, 1);
@@ -416,6 +433,7 @@ __global__ void __launch_bounds__(256) k_sae_grads(const int* __restrict__ off, 
                                                    float* __restrict__ gb_enc, float* __restrict__ gbdec2, float* __restrict__ fired,
                                                    SaeScalars* __restrict__ sc, int F, int d, int k, SaeWorkHeader* __restrict__ work,
                                                    int* __restrict__ work_feats, int* __restrict__ work_chunks) {
+  pb_pdl();
   extern __shared__ __align__(16) float sm_bd[];  // [d] per-CTA partial of gbdec2
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nvec = d >> 2;
@@ -567,6 +585,7 @@ __global__ void __launch_bounds__(256) k_sae_grads_long(const int* __restrict__ 
                                                         float* __restrict__ gW_dec, float* __restrict__ gW_encT, float* __restrict__ gb_enc,
                                                         float* __restrict__ gbdec2, float* __restrict__ fired, int d, int k,
                                                         const SaeWorkHeader* __restrict__ work, const int* __restrict__ work_chunks) {
+  pb_pdl();
   extern __shared__ __align__(16) float sm_bd[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nvec = d >> 2;
@@ -650,6 +669,7 @@ __global__ void __launch_bounds__(256) k_sae_grads_long(const int* __restrict__ 
 __global__ void __launch_bounds__(256) k_sae_norm_long(const float* __restrict__ gW_dec, const float* __restrict__ gW_encT,
                                                        const float* __restrict__ gb_enc, SaeScalars* __restrict__ sc, int d,
                                                        const SaeWorkHeader* __restrict__ work, const int* __restrict__ work_feats) {
+  pb_pdl();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int n = work->n_long;
   float nsq = 0.f;
@@ -673,6 +693,7 @@ __global__ void k_sae_gbdec(const float* __restrict__ gcol, const float* __restr
 // 6. finalize: gb_dec = colsum(g) - gbdec2 ; total norm ; clip coefficient (train_sae.py:394-397)
 __global__ void __launch_bounds__(256) k_sae_finalize(const float* __restrict__ gcol, const float* __restrict__ gbdec2, float* __restrict__ gb_dec,
                                                       SaeScalars* __restrict__ sc, int d, float max_norm, float inv_elems, float inv_rows) {
+  pb_pdl();
   __shared__ float red[8];
   float s = 0.f;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -850,6 +871,7 @@ k_sae_adam_bulk(float* __restrict__ W_dec, float* __restrict__ W_encT, float* __
                 const float* __restrict__ fired, float* __restrict__ since_fired, float* __restrict__ act_freq,
                 const SaeScalars* __restrict__ sc, AdamHyper h, int F, int d, int renorm, float* __restrict__ enc_norm_max, int S,
                 float* __restrict__ b_dec, const float* __restrict__ gb_dec, float* __restrict__ m_bd, float* __restrict__ v_bd) {
+  pb_pdl_trigger();
   extern __shared__ __align__(128) unsigned char ab_smem[];
   const uint32_t s0 = smem_u32(ab_smem);
   const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = 8u * row_bytes;
@@ -864,6 +886,7 @@ k_sae_adam_bulk(float* __restrict__ W_dec, float* __restrict__ W_encT, float* __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pb_pdl_wait();                                   // gradients / clip coefficient of the preceding kernels are complete
   if (warp == 0) {
     if (blockIdx.x == 0 && b_dec) {                 // the decoder bias (d values): this warp, before it turns producer
       const float clip0 = sc->clip_coef;
@@ -1094,12 +1117,11 @@ extern "C" int pb_sae_prep(const float* x, const float* b_dec, float* sae_in, fl
   if (rows == 0) return PB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int ch = chunks_for(d);
-  PB_DISPATCH_CHUNKS(ch, (k_sae_prep<C_><<<(rows + 7) / 8, 256, 0, st>>>(x, b_dec, sae_in, sae_in_lo, mu, sd, rows, d, norm_mode, 1e-5f)));
-  PB_LAUNCH_CHECK();
+  PB_DISPATCH_CHUNKS(ch, PB_LAUNCH_PDL(k_sae_prep<C_>, (rows + 7) / 8, 256, 0, st, x, b_dec, sae_in, sae_in_lo, mu, sd, rows, d, norm_mode, 1e-5f));
   if (xsum) {
     PB_CUDA(cudaMemsetAsync(xsum, 0, sizeof(float) * d, st));
-    const int rpc = 32;
-    k_colsum<<<(rows + rpc - 1) / rpc, 256, 0, st>>>(x, xsum, rows, d, rpc);
+    const int rpc = 8;
+    k_colsum<<<(rows + rpc - 1) / rpc, 256, 0, st>>>(x, xsum, rows, d, rpc);     // after a memset: a plain launch
     PB_LAUNCH_CHECK();
   }
   return PB_OK;
@@ -1169,6 +1191,7 @@ __global__ void k_sae_fwd_scalars(SaeScalars* sc, float inv_elems, float inv_row
 // every accumulator a training step starts from zero, in one launch (they were six memsets / fills on the stream)
 __global__ void __launch_bounds__(256) k_sae_step_reset(float* __restrict__ feat_count, int F, float* __restrict__ scalars, float* __restrict__ gcol,
                                                         float* __restrict__ gbdec2, int d, int* __restrict__ work_hdr, int* __restrict__ fb_count) {
+  pb_pdl();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   for (int f = i; f < F; f += gridDim.x * blockDim.x) feat_count[f] = 0.f;
   if (i < d) { gcol[i] = 0.f; gbdec2[i] = 0.f; }
@@ -1184,8 +1207,7 @@ extern "C" int pb_sae_step_reset(const PbSaeStep* s, int32_t* fb_count, pb_strea
   int grid = (n + 255) / 256;
   if (grid > pb_sm_count() * 2) grid = pb_sm_count() * 2;
   if (grid * 256 < s->d) grid = (s->d + 255) / 256;
-  k_sae_step_reset<<<grid, 256, 0, (cudaStream_t)stream>>>(s->feat_count, s->F, (float*)s->scalars, s->gcol, s->gbdec2, s->d, (int*)s->work, fb_count);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH_PDL(k_sae_step_reset, grid, 256, 0, (cudaStream_t)stream, s->feat_count, s->F, (float*)s->scalars, s->gcol, s->gbdec2, s->d, (int*)s->work, fb_count);
   return PB_OK;
 }
 
@@ -1195,10 +1217,9 @@ extern "C" int pb_sae_decode(const PbSaeStep* s, pb_stream_t stream) {
   if (s->rows == 0) return PB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int d = s->d, ch = chunks_for(d);
-  PB_DISPATCH_CHUNKS(ch, (k_sae_decode<C_><<<(s->rows + 7) / 8, 256, 0, st>>>(
+  PB_DISPATCH_CHUNKS(ch, PB_LAUNCH_PDL(k_sae_decode<C_>, (s->rows + 7) / 8, 256, 0, st,
       s->x, s->xsum, s->mu, s->sd, s->idx, s->val, s->W_dec, s->b_dec, s->sae_out, s->g, s->dval, (SaeScalars*)s->scalars, s->rows, d, s->k,
-      s->norm_mode, s->training, 1.f / (float)(s->global_rows > 0 ? s->global_rows : s->rows))));
-  PB_LAUNCH_CHECK();
+      s->norm_mode, s->training, 1.f / (float)(s->global_rows > 0 ? s->global_rows : s->rows)));
   if (!s->training) {  // inference: publish mse / l0 now (the training path does it in k_sae_finalize)
     k_sae_fwd_scalars<<<1, 1, 0, st>>>((SaeScalars*)s->scalars, 1.f / ((float)s->rows * (float)d), 1.f / (float)s->rows);
     PB_LAUNCH_CHECK();
@@ -1213,18 +1234,23 @@ extern "C" int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream) {
   if (s->rows == 0) return PB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int d = s->d, F = s->F, ch = chunks_for(d);
-  k_scan_counts<<<1, 1024, 0, st>>>(s->feat_count, s->csc_off, s->csc_cursor, F);
-  PB_LAUNCH_CHECK();
+  {
+    const int per = ((F + 1023) / 1024 + 3) / 4 * 4;
+    PB_CHECK_ARG(per <= 128, "pb_sae_backward: d_sae=%d too large for the offset scan (max 131072)", F);
+    if (per <= 8) PB_LAUNCH_PDL(k_scan_counts<8>, 1, 1024, 0, st, s->feat_count, s->csc_off, s->csc_cursor, F);
+    else if (per <= 24) PB_LAUNCH_PDL(k_scan_counts<24>, 1, 1024, 0, st, s->feat_count, s->csc_off, s->csc_cursor, F);
+    else if (per <= 48) PB_LAUNCH_PDL(k_scan_counts<48>, 1, 1024, 0, st, s->feat_count, s->csc_off, s->csc_cursor, F);
+    else if (per <= 64) PB_LAUNCH_PDL(k_scan_counts<64>, 1, 1024, 0, st, s->feat_count, s->csc_off, s->csc_cursor, F);
+    else PB_LAUNCH_PDL(k_scan_counts<128>, 1, 1024, 0, st, s->feat_count, s->csc_off, s->csc_cursor, F);
+  }
   const int64_t n = (int64_t)s->rows * s->k;
-  k_csc_fill<<<pb_sm_count() * 4, 256, 0, st>>>(s->idx, s->csc_cursor, s->csc_entries, n);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH_PDL(k_csc_fill, pb_sm_count() * 4, 256, 0, st, (const int*)s->idx, s->csc_cursor, s->csc_entries, n);
   if (!s->pre_zeroed) {
     PB_CUDA(cudaMemsetAsync(s->gcol, 0, sizeof(float) * d, st));
     PB_CUDA(cudaMemsetAsync(s->gbdec2, 0, sizeof(float) * d, st));
   }
-  const int rpc = 32;
-  k_colsum<<<(s->rows + rpc - 1) / rpc, 256, 0, st>>>(s->g, s->gcol, s->rows, d, rpc);
-  PB_LAUNCH_CHECK();
+  const int rpc = 8;     // 512 CTAs at 4096 rows: the 32-row version ran 128 CTAs of 32 dependent-latency trips (10.7 us)
+  PB_LAUNCH_PDL(k_colsum, (s->rows + rpc - 1) / rpc, 256, 0, st, (const float*)s->g, s->gcol, s->rows, d, rpc);
   // work area for hot features: header | work_feats[F] | work_chunks[2 * (rows*k / CHUNK + F + 1)]
   const int64_t cap = n / SAE_LONG_CHUNK + F + 1;
   const int64_t need = (int64_t)sizeof(SaeWorkHeader) + 4 * (int64_t)F + 8 * cap;
@@ -1235,27 +1261,21 @@ extern "C" int pb_sae_backward(const PbSaeStep* s, pb_stream_t stream) {
   int* work_chunks = work_feats + F;
   if (!s->pre_zeroed) PB_CUDA(cudaMemsetAsync(wh, 0, sizeof(SaeWorkHeader), st));
   const int grid = persistent_grid(8, F);
-  PB_DISPATCH_CHUNKS(ch, (k_sae_grads<C_><<<grid, 256, sizeof(float) * d, st>>>(s->csc_off, s->csc_entries, s->val, s->dval, s->g, s->sae_in,
-                                                                                s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc, s->gbdec2,
-                                                                                s->fired, (SaeScalars*)s->scalars, F, d, s->k, wh, work_feats,
-                                                                                work_chunks)));
-  PB_LAUNCH_CHECK();
-  PB_DISPATCH_CHUNKS(ch, (k_sae_grads_long<C_><<<pb_sm_count() * 4, 256, sizeof(float) * d, st>>>(
-                             s->csc_off, s->csc_entries, s->val, s->dval, s->g, s->sae_in, s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc,
-                             s->gbdec2, s->fired, d, s->k, wh, work_chunks)));
-  PB_LAUNCH_CHECK();
+  PB_DISPATCH_CHUNKS(ch, PB_LAUNCH_PDL(k_sae_grads<C_>, grid, 256, sizeof(float) * d, st, s->csc_off, s->csc_entries, s->val, s->dval, s->g, s->sae_in,
+                                       s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc, s->gbdec2, s->fired, (SaeScalars*)s->scalars, F, d, s->k, wh,
+                                       work_feats, work_chunks));
+  PB_DISPATCH_CHUNKS(ch, PB_LAUNCH_PDL(k_sae_grads_long<C_>, pb_sm_count() * 4, 256, sizeof(float) * d, st, s->csc_off, s->csc_entries, s->val, s->dval,
+                                       s->g, s->sae_in, s->W_encT, s->gW_dec, s->gW_encT, s->gb_enc, s->gbdec2, s->fired, d, s->k, wh, work_chunks));
   if (!s->dist) {
-    k_sae_norm_long<<<pb_sm_count(), 256, 0, st>>>(s->gW_dec, s->gW_encT, s->gb_enc, (SaeScalars*)s->scalars, d, wh, work_feats);
-    PB_LAUNCH_CHECK();
+    PB_LAUNCH_PDL(k_sae_norm_long, pb_sm_count(), 256, 0, st, s->gW_dec, s->gW_encT, s->gb_enc, (SaeScalars*)s->scalars, d, wh, work_feats);
   }
   if (s->dist) {  // data parallel: only the local gb_dec; norm / clip happen after the peer reduction (p2p.cu)
     k_sae_gbdec<<<(d + 255) / 256, 256, 0, st>>>(s->gcol, s->gbdec2, s->gb_dec, d);
     PB_LAUNCH_CHECK();
     return PB_OK;
   }
-  k_sae_finalize<<<1, 256, 0, st>>>(s->gcol, s->gbdec2, s->gb_dec, (SaeScalars*)s->scalars, d, s->max_grad_norm,
-                                    1.f / ((float)s->rows * (float)d), 1.f / (float)s->rows);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH_PDL(k_sae_finalize, 1, 256, 0, st, s->gcol, s->gbdec2, s->gb_dec, (SaeScalars*)s->scalars, d, s->max_grad_norm,
+                1.f / ((float)s->rows * (float)d), 1.f / (float)s->rows);
   return PB_OK;
 }
 
@@ -1286,9 +1306,9 @@ extern "C" int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream) {
   do {                                                                                                                                \
     auto kern = k_sae_adam_bulk<CH>;                                                                                                  \
     PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                     \
-    kern<<<g2, 32 * (1 + S), smem, st>>>(s->W_dec, s->W_encT, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc, s->m_dec, s->v_dec, s->m_enc, \
-                                       s->v_enc, s->m_be, s->v_be, s->fired, s->since_fired, s->act_freq, (const SaeScalars*)s->scalars, \
-                                       h, F, d, s->renorm_decoder, s->enc_norm_max, S, s->b_dec, s->gb_dec, s->m_bd, s->v_bd);         \
+    PB_LAUNCH_PDL(kern, g2, 32 * (1 + S), smem, st, s->W_dec, s->W_encT, s->b_enc, s->gW_dec, s->gW_encT, s->gb_enc, s->m_dec, s->v_dec, s->m_enc, \
+                  s->v_enc, s->m_be, s->v_be, s->fired, s->since_fired, s->act_freq, (const SaeScalars*)s->scalars,                    \
+                  h, F, d, s->renorm_decoder, s->enc_norm_max, S, s->b_dec, s->gb_dec, s->m_bd, s->v_bd);                               \
   } while (0)
       switch (ch) {
         case 1: PB_ADAM_BULK(1); break;
@@ -1300,7 +1320,6 @@ extern "C" int pb_sae_adam(const PbSaeStep* s, pb_stream_t stream) {
         default: pb_set_error("sae: d_in=%d unsupported", d); return PB_EUNSUPPORTED;
       }
 #undef PB_ADAM_BULK
-      PB_LAUNCH_CHECK();
       return PB_OK;
     }
   }

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_enc_cand(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, int M, int N,
            const float* __restrict__ bias, int* __restrict__ cand, int num_m_tiles, int num_n_tiles) {
   using C = FzCfg;
+  pb_pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = smem_u32(smem_raw);
   const uint32_t ring = (smem0 + 1023u) & ~1023u;
@@ -79,6 +80,7 @@ k_enc_cand(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_generic;
+  pb_pdl_wait();            // barriers initialised, TMEM allocated, tensor maps prefetched: now the prep kernel's sae_in must be complete
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(256) k_cand_select(const int* __restrict__ can
                                                      const float* __restrict__ wnorm_max, float err_scale, int d, int k, int m_cand,
                                                      int* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ feat_count,
                                                      int* __restrict__ fb_count, int* __restrict__ fb_rows, int* __restrict__ stats) {
+  pb_pdl();
   extern __shared__ __align__(16) unsigned char sm_raw[];
   float* a_row = reinterpret_cast<float*>(sm_raw);
   __shared__ unsigned long long items[SEL_SLOTS];
@@ -436,6 +439,7 @@ __global__ void __launch_bounds__(256) k_topk_fallback(const int* __restrict__ f
                                                        const float* __restrict__ sae_in, const float* __restrict__ W_encT,
                                                        const float* __restrict__ b_enc, float* __restrict__ scratch, int d, int F, int k, int cap,
                                                        int* __restrict__ out_idx, float* __restrict__ out_val, float* __restrict__ feat_count) {
+  pb_pdl();
   const int n_items = *fb_count;
   if (n_items == 0) return;
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -541,17 +545,15 @@ int launch_enc_cand(const PbSaeEncode* e, cudaStream_t st) {
   const int num_m = (e->rows + TC_BM - 1) / TC_BM, num_n = (e->F + FZ_BN - 1) / FZ_BN;
   int grid = pb_sm_count();
   if (grid > num_m * num_n) grid = num_m * num_n;
-  kern<<<grid, FZ_THREADS, FZ_SMEM, st>>>(tmA, tmB, e->d, e->rows, e->F, e->b_enc, e->cand, num_m, num_n);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH_PDL(kern, grid, FZ_THREADS, FZ_SMEM, st, tmA, tmB, e->d, e->rows, e->F, e->b_enc, e->cand, num_m, num_n);
   return PB_OK;
 }
 
 template <int SPT>
 int launch_select(const PbSaeEncode* e, int nseg, float scale, cudaStream_t st) {
   const size_t smem = sizeof(float) * e->d;
-  k_cand_select<SPT><<<e->rows, 256, smem, st>>>(e->cand, nseg, e->c_keep, e->sae_in, e->W_encT, e->b_enc, e->enc_norm_max, scale, e->d, e->k,
-                                                  e->m_cand, e->idx, e->val, e->feat_count, e->fb_count, e->fb_rows, e->fb_count + 1);
-  PB_LAUNCH_CHECK();
+  PB_LAUNCH_PDL(k_cand_select<SPT>, e->rows, 256, smem, st, (const int*)e->cand, nseg, e->c_keep, e->sae_in, e->W_encT, e->b_enc, e->enc_norm_max, scale,
+                e->d, e->k, e->m_cand, e->idx, e->val, e->feat_count, e->fb_count, e->fb_rows, e->fb_count + 1);
   return PB_OK;
 }
 
@@ -607,9 +609,8 @@ extern "C" int pb_sae_encode_topk_fused(const PbSaeEncode* e, pb_stream_t stream
       PB_CUDA(cudaFuncSetAttribute(k_topk_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem = smem;
     }
-    k_topk_fallback<<<grid, 256, smem, st>>>(e->fb_count, e->fb_rows, e->sae_in, e->W_encT, e->b_enc, e->fb_scratch, e->d, e->F, e->k, cap, e->idx,
-                                             e->val, e->feat_count);
-    PB_LAUNCH_CHECK();
+    PB_LAUNCH_PDL(k_topk_fallback, grid, 256, smem, st, (const int*)e->fb_count, (const int*)e->fb_rows, e->sae_in, e->W_encT, e->b_enc, e->fb_scratch,
+                  e->d, e->F, e->k, cap, e->idx, e->val, e->feat_count);
   }
   return PB_OK;
 }
