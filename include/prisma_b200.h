@@ -380,6 +380,9 @@ typedef struct {
    * [rank] above are this rank's own (unicast) mappings of the same memory, entries of other ranks are unused.             */
   const float *mc_gW_dec, *mc_gW_encT;
   float *mc_W_dec, *mc_W_encT, *mc_b_enc;
+  /* 1: pb_p2p_adam_allgather updates the owned W_dec rows in the local copy only; pb_p2p_push_dec (any stream, followed by its own
+   * barrier) sends them to the peers later -- the next step reads W_dec only at its decode                                */
+  int32_t defer_dec;
 } PbP2PStep;
 PB_API int pb_p2p_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* cudaMalloc (zeroed) + 64-byte IPC handle */
 PB_API int pb_p2p_open(const unsigned char* handle64, void** peer_ptr);
@@ -392,6 +395,7 @@ PB_API int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream);
 /* after the barrier that follows pb_p2p_adam_allgather: enc_norm_max[0..1] (PbSaeEncode.enc_norm_max) = max over ranks of the
  * encoder row-norm maxima each rank measured on its owned rows; norm_parts must hold 3 * PB_P2P_MAX_RANKS floats, part_accum 4 */
 PB_API int pb_p2p_wmax(const PbP2PStep* s, float* enc_norm_max, pb_stream_t stream);
+PB_API int pb_p2p_push_dec(const PbP2PStep* s, pb_stream_t stream);        /* the deferred W_dec half of the all-gather (defer_dec = 1) */
 /* NVSwitch multicast memory (csrc/mc.cu).  Collective protocol, driven from the host side (vit_prisma/b200/p2p.py):
  *   every rank pb_mc_supported -> rank 0 pb_mc_create (fd) -> fd to the other ranks (SCM_RIGHTS) -> pb_mc_import ->
  *   every rank pb_mc_add_device -> barrier -> every rank pb_mc_bind_alloc -> barrier.  PB_EUNSUPPORTED = fall back.      */

@@ -146,13 +146,22 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PTables t, int f0,
       }
       continue;
     }
+    // peer loads (NVLink): a load from a peer is a ~2 us round trip, so all of them are issued before the first is consumed (the
+    // first version added them one by one inside a runtime-bounded loop: 489 GB/s at 8 ranks, r2g_bench8_peer).  The sum runs in
+    // rank order, starting from rank 0, on every rank -- the same association everywhere.
+    const float4* src[PB_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < PB_MAX_RANKS; ++r)
+      src[r] = r < t.world ? reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4 : nullptr;
     for (int64_t i = tid; i < n4; i += stride) {
-      float4 acc = own[i];
-      for (int r = 0; r < t.world; ++r) {
-        if (r == t.rank) continue;
-        const float4 v = (reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4)[i];   // peer load (NVLink)
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
+      float4 v[PB_MAX_RANKS];
+#pragma unroll
+      for (int r = 0; r < PB_MAX_RANKS; ++r)
+        if (r < t.world) v[r] = src[r][i];
+      float4 acc = v[0];
+#pragma unroll
+      for (int r = 1; r < PB_MAX_RANKS; ++r)
+        if (r < t.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
       own[i] = acc;
       nsq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
     }
@@ -208,7 +217,8 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
                                                            float* __restrict__ m_dec, float* __restrict__ v_dec, float* __restrict__ m_enc,
                                                            float* __restrict__ v_enc, float* __restrict__ m_be, float* __restrict__ v_be,
                                                            const SaeScalarsP2P* __restrict__ sc, AdamHyperP2P h, float* __restrict__ mc_W_dec,
-                                                           float* __restrict__ mc_W_encT, float* __restrict__ mc_b_enc, float* __restrict__ wmax_accum) {
+                                                           float* __restrict__ mc_W_encT, float* __restrict__ mc_b_enc, float* __restrict__ wmax_accum,
+                                                           int defer_dec) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float enc_best = 0.f, enc_best_lo = 0.f;
   const int nvec = d >> 2;
@@ -258,7 +268,8 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
       if (c4 < nvec) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) w[i][q] = w[i][q] * inv_nrm;
-        if (mc_W_dec) mc_st4(mc_W_dec + base + 4 * c4, w[i]);                              // all-gather: one multicast store
+        if (defer_dec) st4(W_dec + base + 4 * c4, w[i]);                                   // own copy only: pb_p2p_push_dec sends it later
+        else if (mc_W_dec) mc_st4(mc_W_dec + base + 4 * c4, w[i]);                         // all-gather: one multicast store
         else for (int r = 0; r < t.world; ++r) st4(t.W_dec[r] + base + 4 * c4, w[i]);      // all-gather: peer stores
       }
     }
@@ -418,7 +429,7 @@ extern "C" int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream) {
   int grid = pb_sm_count() * 4;
   if (grid > (per + 7) / 8) grid = (per + 7) / 8;
   PB_CHECK_ARG((!s->mc_W_dec == !s->mc_W_encT) && (!s->mc_W_dec == !s->mc_b_enc), "pb_p2p_adam_allgather: all three multicast parameter views or none");
-#define PB_P2P_ADAM(CH) k_p2p_adam_allgather<CH><<<grid, 256, 0, st>>>(t, f0, f1, d, s->gb_enc_red, s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, (const SaeScalarsP2P*)s->scalars, h, s->mc_W_dec, s->mc_W_encT, s->mc_b_enc, s->part_accum + 1)
+#define PB_P2P_ADAM(CH) k_p2p_adam_allgather<CH><<<grid, 256, 0, st>>>(t, f0, f1, d, s->gb_enc_red, s->m_dec, s->v_dec, s->m_enc, s->v_enc, s->m_be, s->v_be, (const SaeScalarsP2P*)s->scalars, h, s->mc_W_dec, s->mc_W_encT, s->mc_b_enc, s->part_accum + 1, s->defer_dec)
   const int nvec = d / 4;
   if (d % 4 != 0 || nvec > 384) { pb_set_error("pb_p2p_adam_allgather: d_in=%d unsupported", d); return PB_EUNSUPPORTED; }
   if (nvec <= 32) PB_P2P_ADAM(1);
@@ -433,6 +444,32 @@ extern "C" int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream) {
   PB_LAUNCH_CHECK();
   k_p2p_small_updates<<<(s->F + 255) / 256, 256, 0, st>>>(s->b_dec, s->gb_dec_red, s->m_bd, s->v_bd, s->fired_red, s->since_fired, s->act_freq,
                                                         (const SaeScalarsP2P*)s->scalars, h, d, s->F);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// Deferred half of the all-gather: the owned W_dec rows -> every peer (or one multicast store).  The next step needs W_dec only at
+// its decode, ~0.35 ms after the encoder matrix, so this runs on a side stream under the next step's prep / encoder GEMM / select.
+__global__ void __launch_bounds__(256) k_p2p_push_dec(P2PTables t, int f0, int f1, int d, float* __restrict__ mc_W_dec) {
+  const int64_t n4 = (int64_t)(f1 - f0) * d / 4, base4 = (int64_t)f0 * d / 4;
+  const float4* own = reinterpret_cast<const float4*>(t.W_dec[t.rank]) + base4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = own[i];
+    if (mc_W_dec) {
+      const float w[4] = {v.x, v.y, v.z, v.w};
+      mc_st4(mc_W_dec + 4 * (base4 + i), w);
+    } else {
+      for (int r = 0; r < t.world; ++r)
+        if (r != t.rank) (reinterpret_cast<float4*>(t.W_dec[r]) + base4)[i] = v;
+    }
+  }
+}
+
+extern "C" int pb_p2p_push_dec(const PbP2PStep* s, pb_stream_t stream) {
+  P2PTables t;
+  PB_TRY(fill_tables(s, &t));
+  const int per = s->F / s->world, f0 = s->rank * per, f1 = f0 + per;
+  k_p2p_push_dec<<<pb_sm_count() * 2, 256, 0, (cudaStream_t)stream>>>(t, f0, f1, s->d, s->mc_W_dec);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

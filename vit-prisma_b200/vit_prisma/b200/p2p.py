@@ -31,6 +31,7 @@ class PbP2PStep(C.Structure):
         + [(n, vp) for n in ("gb_enc_red", "gb_dec_red", "fired_red", "part_accum", "b_dec", "scalars",
                              "m_dec", "v_dec", "m_enc", "v_enc", "m_be", "v_be", "m_bd", "v_bd", "since_fired", "act_freq")]
         + [(n, vp) for n in ("mc_gW_dec", "mc_gW_encT", "mc_W_dec", "mc_W_encT", "mc_b_enc")]     # NVSwitch multicast views (or NULL)
+        + [("defer_dec", i32)]
     )
 
 
@@ -45,6 +46,7 @@ L.register_signatures({
     "pb_p2p_reduce_scatter": (i32, [C.POINTER(PbP2PStep), vp]),
     "pb_p2p_adam_allgather": (i32, [C.POINTER(PbP2PStep), vp]),
     "pb_p2p_wmax": (i32, [C.POINTER(PbP2PStep), vp, vp]),
+    "pb_p2p_push_dec": (i32, [C.POINTER(PbP2PStep), vp]),
     "pb_mc_supported": (i32, [C.POINTER(i32)]),
     "pb_mc_round_size": (i32, [i32, i64, C.POINTER(i64)]),
     "pb_mc_create": (i32, [i32, i64, C.POINTER(u64), C.POINTER(i32)]),
@@ -114,7 +116,12 @@ class P2PGroup:
         import tempfile
         import torch.distributed as dist
         lib = L.get_lib()
-        if os.environ.get("PRISMA_P2P_MULTICAST", "1") == "0" or not (dist.is_available() and dist.is_initialized()):
+        # Opt-in (PRISMA_P2P_MULTICAST=1).  Measured on 2 and 8 B200s (profiles/r02_dp_notes.md): multimem.ld_reduce makes every GPU
+        # send its WHOLE gradient through its link once (the switch pulls each rank's copy of every slice, the requester's own
+        # included), the peer-load reduce-scatter sends (N-1)/N of it; ingress shrinks to 1/N but the links are full duplex, so the
+        # exchange time is the same at 8 ranks (1.151 vs 1.146 ms/step) and worse at 2 (1.20 vs 1.01).
+        if os.environ.get("PRISMA_P2P_MULTICAST", "0") != "1" or not (dist.is_available() and dist.is_initialized()):
+            self.multicast_note = "NVSwitch multicast available with PRISMA_P2P_MULTICAST=1; not faster than peer loads / stores here"
             return None
 
         def all_ok(flag: bool) -> bool:
@@ -205,6 +212,19 @@ class P2PGroup:
         self.epoch += 1
         L.check(L.get_lib().pb_p2p_barrier(C.byref(s), self.epoch, _stream()), "pb_p2p_barrier")
 
+    def barrier2(self, s: PbP2PStep, stream: int) -> None:
+        """Barrier of the side stream: its own flag words ("flags2") and epoch counter, so it can interleave with ``barrier``."""
+        self.epoch2 = getattr(self, "epoch2", 0) + 1
+        flags = s.flags
+        saved = [flags[r] for r in range(MAX_RANKS)]
+        for r, p in enumerate(self.peer_ptr["flags2"]):
+            flags[r] = p
+        try:
+            L.check(L.get_lib().pb_p2p_barrier(C.byref(s), self.epoch2, stream), "pb_p2p_barrier(side)")
+        finally:
+            for r in range(MAX_RANKS):
+                flags[r] = saved[r]
+
 
 class SaeDPEngine(SaeStepEngine):
     """``SaeStepEngine`` whose optimizer step is the NVLink reduce-scatter / sharded Adam / all-gather of csrc/p2p.cu."""
@@ -246,6 +266,7 @@ class SaeDPEngine(SaeStepEngine):
         for name, shape in (("gb_enc", (F,)), ("gb_dec", (d,)), ("fired", (F,)), ("xsum", (d,)), ("norm_parts", (3 * MAX_RANKS,))):
             g.alloc(name, shape)
         g.alloc("flags", (MAX_RANKS,), dtype=torch.int32)
+        g.alloc("flags2", (MAX_RANKS,), dtype=torch.int32)        # barrier of the side stream that finishes the W_dec all-gather
         super().__init__(shared["W_encT"], shared["W_dec"], shared["b_enc"], b_dec.clone().contiguous(), k, **kw)
         # re-point the buffers peers must reach at the shared allocations
         if self.W_encT_lo is not None:                 # dense 3xTF32 encoder: the residual plane is all-gathered with the parameters
@@ -257,6 +278,13 @@ class SaeDPEngine(SaeStepEngine):
         dev = W_dec.device
         self.gb_enc_red, self.gb_dec_red, self.fired_red = torch.zeros(F, device=dev), torch.zeros(d, device=dev), torch.zeros(F, device=dev)
         self.part_accum = torch.zeros(4, device=dev)        # gradient-norm partial + encoder row-norm maxima of the owned slice
+        import os
+        # the W_dec half of the all-gather runs on a side stream under the next step's prep / encoder GEMM / select (it is first
+        # read by the next decode); PRISMA_P2P_OVERLAP=0 keeps the whole all-gather inside the Adam kernel
+        self.overlap_dec = os.environ.get("PRISMA_P2P_OVERLAP", "1") != "0" and g.world > 1
+        self._side = torch.cuda.Stream(device=dev) if self.overlap_dec else None
+        self._ev_adam = torch.cuda.Event() if self.overlap_dec else None
+        self._ev_dec = None                                   # recorded on the side stream once every peer's W_dec rows have landed
         g.connect()
         torch.cuda.synchronize()
 
@@ -275,6 +303,18 @@ class SaeDPEngine(SaeStepEngine):
             s.mc_gW_dec, s.mc_gW_encT = self.mc["gW_dec"], self.mc["gW_encT"]
             s.mc_W_dec, s.mc_W_encT, s.mc_b_enc = self.mc["W_dec"], self.mc["W_encT"], self.mc["b_enc"]
         return s
+
+    def wait_parameters(self) -> None:
+        """Make the current stream wait for the deferred W_dec all-gather of the last step (call before reading W_dec outside
+        ``train_step``: forward(), state_dict(), checkpoints)."""
+        if self._ev_dec is not None:
+            torch.cuda.current_stream().wait_event(self._ev_dec)
+            self._ev_dec = None
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, want_out: bool = True):
+        self.wait_parameters()
+        return super().forward(x, want_out)
 
     def describe_exchange(self) -> str:
         n = self.group.world
@@ -305,13 +345,25 @@ class SaeDPEngine(SaeStepEngine):
         ps = self._p2p_desc(rows, float(lr), since_fired, act_freq)
         g.barrier(ps)
         L.check(lib.pb_p2p_sum_xsum(C.byref(ps), self.xsum.data_ptr(), st), "pb_p2p_sum_xsum")
+        if self._ev_dec is not None:                    # the previous step's W_dec rows from every peer (side stream) must have landed
+            torch.cuda.current_stream().wait_event(self._ev_dec)
+            self._ev_dec = None
         L.check(lib.pb_sae_decode(C.byref(s), st), "pb_sae_decode")
         L.check(lib.pb_sae_backward(C.byref(s), st), "pb_sae_backward")
         g.barrier(ps)                                   # every rank's local gradients are complete
         L.check(lib.pb_p2p_reduce_scatter(C.byref(ps), st), "pb_p2p_reduce_scatter")
         g.barrier(ps)                                   # norm partials published; all peer reads of this step are done
+        ps.defer_dec = 1 if self.overlap_dec else 0
         L.check(lib.pb_p2p_adam_allgather(C.byref(ps), st), "pb_p2p_adam_allgather")
-        g.barrier(ps)                                   # every rank holds the updated parameters
+        if self.overlap_dec:                            # W_dec rows -> peers on the side stream, with its own barrier
+            self._ev_adam.record(torch.cuda.current_stream())
+            self._side.wait_event(self._ev_adam)
+            side = self._side.cuda_stream
+            L.check(lib.pb_p2p_push_dec(C.byref(ps), side), "pb_p2p_push_dec")
+            g.barrier2(ps, side)
+            self._ev_dec = torch.cuda.Event()
+            self._ev_dec.record(self._side)
+        g.barrier(ps)                                   # every rank holds the updated encoder (and, without overlap, decoder) parameters
         if self.encoder == "fused":                     # error bound of the next step's tf32 pass: largest encoder-column norms, merged over ranks
             L.check(lib.pb_p2p_wmax(C.byref(ps), self.enc_norm_max.data_ptr(), st), "pb_p2p_wmax")
         return self.scalars
