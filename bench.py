@@ -43,7 +43,8 @@ sys.path.insert(0, os.path.join(ROOT, "vit-prisma_b200"))
 
 import torch  # noqa: E402
 
-SAE_CFG = dict(d_in=768, expansion=32, k=32, batch=4096)     # BASELINE.json configs[2]
+SAE_CFG = dict(d_in=768, expansion=32, k=32, batch=4096, dtype="float32")     # BASELINE.json configs[2]
+SAE_CFG5 = dict(d_in=768, expansion=128, k=32, batch=4096, dtype="bfloat16")  # BASELINE.json configs[4]: dict 768x128, bf16, data parallel
 POOL_BATCHES = 16                                            # synthetic activation pool = 16 steps' worth of tokens (201 MB > L2)
 
 
@@ -251,7 +252,7 @@ def run_reference_arm(args):
     steps, warm = args.steps, args.warmup
     threads = _cpu_cores()
     torch.set_num_threads(threads)
-    if args.workload in ("all", "sae"):
+    if args.workload in ("all", "sae", "cfg5"):      # cfg5's reference leg is the headline SAE sample (the oracle is fp32, d_sae 24576)
         from oracle.sae_oracle import sae_train_step
         batch = 1024   # bounded sample of the 4096-token step: the dense products are linear in the token count
         p, state, x = _cpu_sae_setup(batch)
@@ -527,13 +528,18 @@ def build_sae_trainer(ctx, cfg, store, group=None, init=None):
     return trainer
 
 
-def run_sae(args, ctx):
+def run_sae(args, ctx, spec=None):
+    """``spec`` = SAE_CFG (the headline, configs[2]) or SAE_CFG5 (configs[4]: bf16 storage -- parameters, state dict and activations
+    in bf16; the step engine trains fp32 masters and exports the rounded parameters every step, vit_prisma/sae/sae.py)."""
     from vit_prisma.b200 import _lib as L
     from vit_prisma.b200.synthetic import activation_pool
+    spec = spec or SAE_CFG
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
-    d, F, k, Bt = SAE_CFG["d_in"], SAE_CFG["d_in"] * SAE_CFG["expansion"], SAE_CFG["k"], SAE_CFG["batch"]
-    cfg = sae_runner_cfg(d, SAE_CFG["expansion"], k, Bt)
-    pool_host = activation_pool(Bt * POOL_BATCHES, d, seed=rank).pin_memory()        # every rank: its own token shard
+    d, F, k, Bt = spec["d_in"], spec["d_in"] * spec["expansion"], spec["k"], spec["batch"]
+    low = spec["dtype"] != "float32"
+    act_dtype = torch.bfloat16 if low else torch.float32
+    cfg = sae_runner_cfg(d, spec["expansion"], k, Bt, _dtype=spec["dtype"])
+    pool_host = activation_pool(Bt * POOL_BATCHES, d, seed=rank).to(act_dtype).pin_memory()        # every rank: its own token shard
     store = _PoolStore(pool_host.to(dev), Bt)
     group = None
     if world > 1:      # data parallel over NVLink peer memory: Bt tokens per GPU, one global step (csrc/p2p.cu)
@@ -633,18 +639,23 @@ def run_sae(args, ctx):
             "algorithmic_bytes": step_bytes, "peak_source": peaks["source"] + " HBM copy bandwidth",
             "dominant_kernel": dom, "stages": kernels}
     cpu = cpu_sae_tokens_per_sec()
-    rec = {"metric": SAE_METRIC, "value": value, "unit": "tokens/s", "n_gpus": world,
+    mb = d * F * 4 / 1e6
+    metric = SAE_METRIC if spec is SAE_CFG else f"SAE training tokens/sec (TopK SAE, d_model={d}, dict={d}x{spec['expansion']}, k={k}, {spec['dtype']})"
+    rec = {"metric": metric, "value": value, "unit": "tokens/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-           "config": {"workload": "sae_topk_train_step", "api": "VisionSAETrainer.train_step", "d_in": d, "d_sae": F, "k": k,
+           "vs_baseline": None, "dtype": "fp32" if not low else "bf16 storage (parameters, activations) / fp32 masters, moments and arithmetic",
+           "data": "synthetic",
+           "config": {"workload": "sae_topk_train_step" if spec is SAE_CFG else "sae_topk_train_step_cfg5", "api": "VisionSAETrainer.train_step",
+                      "d_in": d, "d_sae": F, "k": k,
                       "tokens_per_step_per_gpu": Bt, "global_batch": Bt * world, "engine": type(eng).__name__,
                       "encoder": eng.describe_encoder(), "normalize_activations": "layer_norm", "max_grad_norm": 1.0,
-                      "l2": "working set (2 x 75 MB weights + 2 x 150 MB Adam state + 150 MB gradients + 201 MB activation pool) larger than L2",
+                      "l2": f"working set (2 x {mb:.0f} MB weights + 2 x {2 * mb:.0f} MB Adam state + {2 * mb:.0f} MB gradients + "
+                            f"{POOL_BATCHES * Bt * d * pool_host.element_size() / 1e6:.0f} MB activation pool) larger than L2",
                       "parallelism": f"dp{world}" + (" (reduce-scatter + sharded Adam + all-gather over NVLink, no NCCL on the data path; "
                                                       + eng.describe_exchange() + ")" if world > 1 else "")},
            "clocks": clocks.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
            "final_loss": final_loss,
-           "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * 4, "d2h_bytes_per_step": 4,
+           "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * pool_host.element_size(), "d2h_bytes_per_step": 4,
                    "ms_per_step": e2e_ms / args.steps, "host_enqueue_ms_per_step": e2e_host_ms,
                    "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},
            "roofline": roof, "cpu_baseline": cpu}
@@ -806,7 +817,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "sae", "vit", "cfg4"],
+    ap.add_argument("--workload", default="all", choices=["all", "sae", "vit", "cfg4", "cfg5"],
                     help="all (default) = SAE training step as the headline record + the full run_with_cache record under 'secondary'")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="ViT model dtype (the SAE step is fp32)")
     ap.add_argument("--batch", type=int, default=512, help="ViT images per step per GPU")
@@ -824,6 +835,8 @@ def main():
         line = None
         if args.workload == "cfg4":
             line = run_cfg4(args, ctx)
+        if args.workload == "cfg5":
+            line = run_sae(args, ctx, spec=SAE_CFG5)
         if args.workload in ("all", "sae"):
             line = run_sae(args, ctx)
             if ctx.world > 1:

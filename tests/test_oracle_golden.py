@@ -159,3 +159,23 @@ def test_geometric_median_matches_reference_fixture():
         assert err <= 1e-5, (case["seed"], err)
         if case["outliers"]:
             assert (case["median"] - case["mean"]).norm() > 0.1          # the fixture really distinguishes median from mean
+
+
+def test_sae_oracle_follows_the_fp32_twin_of_the_bf16_fixture():
+    """sae_bf16_v.pt (cfg #5 shape class): the reference run in fp32 from bf16-rounded initial parameters and data -- the trajectory
+    the product's fp32-master step must follow -- is reproduced by the oracle; its bf16 run stays within bf16 noise of it."""
+    gold = load_golden("sae_bf16_v.pt")
+    p = {k: v.float().clone() for k, v in gold["init"].items()}
+    state = new_adam_state(p)
+    data, B, k = gold["data"].float(), gold["batch"], gold["k"]
+    for s, (rec16, rec32) in enumerate(zip(gold["steps"], gold["steps_fp32"])):
+        lr = gold["lr"] * lr_multiplier(s, gold["warm_up_steps"], gold["total_steps"], gold["lr_end"])
+        assert abs(lr - rec32["lr"]) < 1e-12
+        out = sae_train_step(p, state, data[s * B:(s + 1) * B], k, lr, s + 1, mode=gold["norm"])
+        assert abs(out["mse"].item() - rec32["mse"]) <= 1e-5 * abs(rec32["mse"])
+        assert abs(out["grad_norm"].item() - rec32["grad_norm"]) <= 1e-4 * rec32["grad_norm"]
+        assert_close(out["fwd"]["sae_out"], rec32["sae_out"], 1e-5, f"step {s} sae_out")
+        for n in p:
+            assert_close(p[n], rec32["params_after"][n], 2e-5, f"step {s} param {n}")
+        assert abs(rec16["mse"] - rec32["mse"]) <= 1e-2 * rec32["mse"]
+        assert rec16["params_after"]["W_dec"].dtype == torch.bfloat16

@@ -1,0 +1,79 @@
+"""cfg #5 shape class: a bfloat16 SAE (``_dtype="bfloat16"``) trained through VisionSAETrainer.train_step.
+
+Storage is what the reference's would be (bf16 nn.Parameters / state dict / activations); the optimizer math, the Adam moments and
+the accumulated parameters are fp32 masters inside the step engine (the reference keeps bf16 only).  The fixture
+(tests/golden/make_golden_sae_bf16.py, unmodified reference + a one-entry dtype_mapping shim) holds two trajectories from the same
+bf16 initial state: the reference in bf16 and the reference in fp32.  Bars:
+  * step-0 reconstruction on identical bf16 weights: within 1e-2 of the reference's bf16 output (north_star bf16 bar);
+  * losses: within 1e-2 of the reference's bf16 run, within 1e-4 of its fp32 run (our arithmetic is the fp32 one);
+  * parameters after every step: bf16 tensors, no further from the fp32 trajectory than one bf16 rounding (2^-8 relative), and never
+    further from it than the reference's own bf16 run is.
+"""
+import contextlib
+import io
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.util import load_golden, rel_err  # noqa: E402
+
+
+def _trainer(gold):
+    from vit_prisma.sae.config import VisionModelSAERunnerConfig
+    from vit_prisma.sae.train_sae import VisionSAETrainer
+    with contextlib.redirect_stdout(io.StringIO()):
+        cfg = VisionModelSAERunnerConfig(d_in=gold["d_in"], expansion_factor=gold["d_sae"] // gold["d_in"], activation_fn_str="topk",
+                                         activation_fn_kwargs={"k": gold["k"]}, _device="cuda", _dtype="bfloat16",
+                                         normalize_activations=gold["norm"], b_dec_init_method="zeros", lr=gold["lr"],
+                                         lr_warm_up_steps=gold["warm_up_steps"], train_batch_size=gold["batch"], max_grad_norm=1.0,
+                                         initialization_method="independent", log_to_wandb=False, n_checkpoints=0,
+                                         checkpoint_path="/tmp/prisma_b200_unused", num_epochs=1)
+    cfg.total_training_steps = gold["total_steps"]
+    trainer = VisionSAETrainer(cfg, model=None, dataset=None, activations_store=object())
+    sae = trainer.sparse_coder
+    sae.load_state_dict({k: v.cuda() for k, v in gold["init"].items()})
+    return cfg, trainer, sae
+
+
+def test_bf16_sae_trains_on_fp32_masters_and_exports_bf16_parameters():
+    gold = load_golden("sae_bf16_v.pt")
+    cfg, trainer, sae = _trainer(gold)
+    assert all(v.dtype == torch.bfloat16 for v in sae.state_dict().values())
+    data = gold["data"].cuda()
+    B = gold["batch"]
+    # step-0 reconstruction through the module's own forward (bf16 weights identical to the reference's)
+    sae.eval()
+    out0 = sae(data[:B])[0]
+    assert out0.dtype == torch.bfloat16
+    assert rel_err(out0.float().cpu(), gold["steps"][0]["sae_out"].float()) <= 1e-2
+    act_freq, since_fired, n_frac, opt, sched = trainer.initialize_training_variables()
+    for s, (rec16, rec32) in enumerate(zip(gold["steps"], gold["steps_fp32"])):
+        x = data[s * B:(s + 1) * B].unsqueeze(1)
+        loss, mse, l1, l0, act_freq, since_fired, n_frac = trainer.train_step(sae, opt, sched, act_freq, since_fired, n_frac, x, s, s * B)
+        assert abs(mse.item() - rec32["mse"]) <= 1e-4 * rec32["mse"], (s, mse.item(), rec32["mse"])
+        assert abs(mse.item() - rec16["mse"]) <= 1e-2 * rec16["mse"], (s, mse.item(), rec16["mse"])
+        assert abs(l0.item() - rec32["l0"]) < 1e-5
+        sd = sae.state_dict()
+        for name, ref32 in rec32["params_after"].items():
+            mine = sd[name]
+            assert mine.dtype == torch.bfloat16, name
+            if name == "W_dec":                                   # the step leaves the rows unit-norm; the reference renormalises at its next step
+                ref32 = ref32 / ref32.norm(dim=1, keepdim=True)
+                ref16 = rec16["params_after"][name].float()
+                ref16 = ref16 / ref16.norm(dim=1, keepdim=True)
+            else:
+                ref16 = rec16["params_after"][name].float()
+            scale = float(ref32.abs().max())
+            ours = float((mine.float().cpu() - ref32).abs().max())
+            theirs = float((ref16 - ref32).abs().max())
+            assert ours <= 2.0 ** -8 * scale + 1e-7, f"step {s} {name}: {ours:.3e} from the fp32 trajectory (one bf16 rounding = {2.0 ** -8 * scale:.3e})"
+            assert ours <= theirs + 2.0 ** -9 * scale + 1e-7, f"step {s} {name}: further from the fp32 trajectory ({ours:.3e}) than the reference's bf16 run ({theirs:.3e})"
+    # the masters follow a load_state_dict (version check), and the module forward sees the trained parameters
+    eng = sae.step_engine()
+    assert eng.W_dec.dtype == torch.float32 and eng.m_dec.dtype == torch.float32
+    assert rel_err(sae.W_dec.data.float(), eng.W_dec) <= 2.0 ** -8
+    sae.load_state_dict({k: v.cuda() for k, v in gold["init"].items()})
+    eng2 = sae.step_engine()
+    assert torch.equal(eng2.W_dec.cpu(), gold["init"]["W_dec"].float())

@@ -135,7 +135,7 @@ def test_clip_b32_bf16_matches_oracle():
     out, cache = model.run_with_cache(x.to(torch.bfloat16).cuda())
     assert model.last_route == "fused"
     assert list(cache.keys()) == list(cache_ref.keys())
-    worst, ours_vs_truth, ref_vs_truth = ("", 0.0), 0.0, 0.0
+    worst, ours_vs_truth, ref_vs_truth, loose = ("", 0.0), 0.0, 0.0, []
     for k, ref in cache_ref.items():
         got = cache[k]
         assert got.dtype == ref.dtype and tuple(got.shape) == tuple(ref.shape), k
@@ -145,6 +145,14 @@ def test_clip_b32_bf16_matches_oracle():
         if k.endswith("hook_resid_post"):
             ours_vs_truth = max(ours_vs_truth, rel_err(got.cpu().float(), cache_true[k]))
             ref_vs_truth = max(ref_vs_truth, rel_err(ref.float(), cache_true[k]))
+        if _bar(k, "bf16") > 1e-2:
+            # every key whose bar is looser than north_star's 1e-2: we must be no further from the fp32 truth than the reference's own
+            # bf16 path is (1.25x + a quarter of a bf16 ulp of slack for the max-norm statistic)
+            mine_t, ref_t = rel_err(got.cpu().float(), cache_true[k]), rel_err(ref.float(), cache_true[k])
+            loose.append((k, mine_t, ref_t))
+            assert mine_t <= 1.25 * ref_t + 1e-3, f"{k}: {mine_t:.2e} vs fp32 truth, the reference's bf16 path has {ref_t:.2e}"
+    print(f"[bf16] {len(loose)} keys with a bar > 1e-2; worst ours/reference distance to the fp32 truth: "
+          f"{max(loose, key=lambda t: t[1] / max(t[2], 1e-9))}")
     print(f"[bf16] worst key {worst[0]} rel err {worst[1]:.2e}; residual stream vs fp32 truth: ours {ours_vs_truth:.2e}, reference-bf16 {ref_vs_truth:.2e}")
     assert ours_vs_truth <= 1.25 * ref_vs_truth + 1e-3, "less accurate than the reference's own bf16 path"
     assert rel_err(out.cpu(), out_ref) <= 2e-2            # same two-ulp budget as the residual stream it is computed from

@@ -117,6 +117,44 @@ __global__ void k_p2p_sum_small(P2PTables t, float* __restrict__ out, int which,
 
 // ------------------------------------------------------------------------------------------- reduce-scatter + norm
 // rows [f0, f1) of both gradient matrices: own += sum of peers; partial ||g||^2 -> every peer's norm_parts[rank]
+// One gradient array's owned slice: own[i] = sum over ranks (rank order) of that rank's copy; returns this thread's share of ||.||^2.
+// W = compile-time rank count (ranks >= t.world are skipped when W is the generic PB_MAX_RANKS), U = elements per trip.
+template <int W, int U>
+__device__ __forceinline__ float rs_peer_slice(const P2PTables& t, int m, int64_t base4, int64_t n4, float4* __restrict__ own, int64_t tid,
+                                               int64_t stride) {
+  const float4* src[W];
+#pragma unroll
+  for (int r = 0; r < W; ++r) src[r] = r < t.world ? reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4 : nullptr;
+  float nsq = 0.f;
+  int64_t i = tid;
+  for (; i + (U - 1) * stride < n4; i += U * stride) {
+    float4 v[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+        if (r < t.world) v[u][r] = src[r][i + u * stride];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float4 acc = v[u][0];
+#pragma unroll
+      for (int r = 1; r < W; ++r)
+        if (r < t.world) { acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w; }
+      own[i + u * stride] = acc;
+      nsq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+    }
+  }
+  for (; i < n4; i += stride) {
+    float4 acc = src[0][i];
+#pragma unroll
+    for (int r = 1; r < W; ++r)
+      if (r < t.world) { const float4 b = src[r][i]; acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w; }
+    own[i] = acc;
+    nsq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+  }
+  return nsq;
+}
+
 __global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PTables t, int f0, int f1, int d, const float* __restrict__ gb_enc_red,
                                                            const float* __restrict__ gb_dec_red, int F, float* __restrict__ part_accum,
                                                            const float* __restrict__ mc_gW_dec, const float* __restrict__ mc_gW_encT) {
@@ -146,25 +184,14 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PTables t, int f0,
       }
       continue;
     }
-    // peer loads (NVLink): a load from a peer is a ~2 us round trip, so all of them are issued before the first is consumed (the
-    // first version added them one by one inside a runtime-bounded loop: 489 GB/s at 8 ranks, r2g_bench8_peer).  The sum runs in
+    // peer loads (NVLink): a load from a peer is a ~2 us round trip, so eight 16-byte loads per thread are issued before the first
+    // is consumed -- all ranks' copies of U = 8 / world consecutive elements (adding them one by one inside a runtime-bounded
+    // loop ran at 489 GB/s at 8 ranks, r2g_bench8_peer; one element per trip at 2 ranks at 409 GB/s, r2i_bench2).  The sum runs in
     // rank order, starting from rank 0, on every rank -- the same association everywhere.
-    const float4* src[PB_MAX_RANKS];
-#pragma unroll
-    for (int r = 0; r < PB_MAX_RANKS; ++r)
-      src[r] = r < t.world ? reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4 : nullptr;
-    for (int64_t i = tid; i < n4; i += stride) {
-      float4 v[PB_MAX_RANKS];
-#pragma unroll
-      for (int r = 0; r < PB_MAX_RANKS; ++r)
-        if (r < t.world) v[r] = src[r][i];
-      float4 acc = v[0];
-#pragma unroll
-      for (int r = 1; r < PB_MAX_RANKS; ++r)
-        if (r < t.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
-      own[i] = acc;
-      nsq += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
-    }
+    if (t.world == 2) nsq += rs_peer_slice<2, 4>(t, m, base4, n4, own, tid, stride);
+    else if (t.world == 4) nsq += rs_peer_slice<4, 2>(t, m, base4, n4, own, tid, stride);
+    else if (t.world == 8) nsq += rs_peer_slice<8, 1>(t, m, base4, n4, own, tid, stride);
+    else nsq += rs_peer_slice<PB_MAX_RANKS, 1>(t, m, base4, n4, own, tid, stride);
   }
   // small vectors are fully reduced on every rank; only rank 0 counts their norm so the global sum counts them once
   if (t.rank == 0) {

@@ -284,3 +284,13 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     y = torch.empty(x.shape, dtype=dtype, device=x.device)
     L.check(L.get_lib().pb_cast(x.data_ptr(), dtype_code(x.dtype), y.data_ptr(), dtype_code(dtype), x.numel(), _stream()), "pb_cast")
     return y
+
+
+def cast_into(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """``out[...] = x`` rounded to ``out.dtype`` (both contiguous, same element count) -- the export of fp32 master
+    parameters into a reduced-precision module's storage."""
+    _need_cuda(x)
+    _need_cuda(out)
+    assert x.is_contiguous() and out.is_contiguous() and x.numel() == out.numel(), "cast_into: contiguous tensors of equal size"
+    L.check(L.get_lib().pb_cast(x.data_ptr(), dtype_code(x.dtype), out.data_ptr(), dtype_code(out.dtype), x.numel(), _stream()), "pb_cast")
+    return out

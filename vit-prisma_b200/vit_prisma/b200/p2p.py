@@ -16,7 +16,7 @@ import torch
 
 from . import _lib as L
 from .ops import _stream
-from .sae_engine import PbSaeEncode, PbSaeStep, SaeStepEngine
+from .sae_engine import PbSaeEncode, PbSaeStep, SaeStepEngine, ops_cast_f32
 
 vp, i32, i64, f32, u32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32, C.c_uint64
 MAX_RANKS = 8
@@ -327,7 +327,7 @@ class SaeDPEngine(SaeStepEngine):
     @torch.no_grad()
     def train_step(self, x: torch.Tensor, lr: float, since_fired=None, act_freq=None, want_out: bool = False) -> torch.Tensor:
         lib, st, g = L.get_lib(), _stream(), self.group
-        x = x.contiguous().float()
+        x = ops_cast_f32(x)
         rows = x.shape[0]
         if getattr(self, "_dp_rows", rows) != rows:
             raise L.PrismaB200Error(f"SaeDPEngine: every step (and every rank) must bring the same number of rows (had {self._dp_rows}, got {rows}); "

@@ -19,7 +19,12 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from .ops import _need_cuda, _stream
+from .ops import _need_cuda, _stream, cast as _cast
+
+
+def ops_cast_f32(x: torch.Tensor) -> torch.Tensor:
+    """Activations arrive in cfg.dtype (bf16 stores for reduced-precision configs); the step kernels read fp32."""
+    return _cast(x.contiguous(), torch.float32)
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -273,7 +278,7 @@ class SaeStepEngine:
     def forward(self, x: torch.Tensor, want_out: bool = True):
         """Inference: encode -> topk -> decode -> mse.  Returns (sae_out | None, idx, val); scalars[3] = mse."""
         _need_cuda(x)
-        x = x.contiguous().float()
+        x = ops_cast_f32(x)
         self.encode_topk(x)
         self.scalars.zero_()
         s = self._desc(x, training=False, want_out=want_out)
@@ -285,7 +290,7 @@ class SaeStepEngine:
                    act_freq: Optional[torch.Tensor] = None, want_out: bool = False) -> torch.Tensor:
         """One optimizer step on batch ``x`` [rows, d].  Returns the 8-float device scalars buffer (no sync)."""
         _need_cuda(x)
-        x = x.contiguous().float()
+        x = ops_cast_f32(x)
         lib, st = L.get_lib(), _stream()
         self._ensure_rows(x.shape[0])
         self.step_count += 1
@@ -326,7 +331,7 @@ class SaeStepEngine:
         (warm caches: shares of the step, not cold-start figures).  Mutates parameters / optimizer state like ``reps`` extra steps.
         Returns ``{stage: {"ms", "bytes" | "flops" (algorithmic, per launch), "ncu" (kernel-name regex for profiles/)}}``."""
         lib, st = L.get_lib(), _stream()
-        x = x.contiguous().float()
+        x = ops_cast_f32(x)
         rows = x.shape[0]
         out = {}
 

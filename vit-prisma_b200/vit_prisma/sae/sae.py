@@ -91,6 +91,7 @@ class SparseAutoencoder(HookedRootModule, ABC):
             self._norm_mode = cfg.normalize_activations
         self.activation_fn = get_activation_fn(cfg.activation_fn_str, **cfg.activation_fn_kwargs)
         self._engine = None
+        self._masters, self._masters_ver = None, None      # fp32 master parameters of reduced-precision configs (StandardSparseAutoencoder)
         self.setup()
 
     # ------------------------------------------------------------------ init helpers
@@ -254,6 +255,49 @@ class StandardSparseAutoencoder(SparseAutoencoder):
             self.W_dec.data = self.W_dec.data.contiguous()
         return self.W_enc.data.t(), self.W_dec.data, self.b_enc.data, self.b_dec.data
 
+    # ------------------------------------------------------------------ reduced-precision configs (cfg.dtype = bfloat16)
+    @property
+    def low_precision(self) -> bool:
+        return self.dtype != torch.float32
+
+    def _param_versions(self):
+        return tuple((p.data_ptr(), p._version) for p in (self.W_enc, self.W_dec, self.b_enc, self.b_dec))
+
+    def _engine_params(self):
+        """The fp32 tensors the step engine trains.  float32 configs: the parameters' own storage.  Reduced-precision configs
+        (cfg #5, ``dtype="bfloat16"``): fp32 MASTER copies -- the reference would run Adam on bf16 parameters with bf16 moments
+        (torch.optim.Adam keeps state in the parameter dtype); here the optimizer math, the moments and the accumulated
+        parameters are fp32 and the module's bf16 nn.Parameters (what state_dict / save_model / forward see) are the masters
+        rounded once per step (``export_masters``).  Masters are rebuilt when someone writes the parameters (load_state_dict)."""
+        if not self.low_precision:
+            return self._canonical_params()
+        wt, wd, be, bd = self._canonical_params()
+        if self._masters is None or self._masters_ver != self._param_versions():
+            self._masters = tuple(ops.cast(t.contiguous(), torch.float32) for t in (wt, wd, be, bd))
+            self._masters_ver = self._param_versions()
+        return self._masters
+
+    @torch.no_grad()
+    def export_masters(self):
+        """Round the fp32 masters into the module's reduced-precision parameter storage (no-op for float32 configs)."""
+        if not self.low_precision or self._masters is None:
+            return
+        eng = self._engine
+        if eng is not None and getattr(eng, "is_data_parallel", False):
+            eng.wait_parameters()                      # the deferred W_dec all-gather lands on a side stream
+        for src, dst in zip(self._masters, self._canonical_params()):
+            ops.cast_into(src, dst)
+
+    @torch.no_grad()
+    def set_decoder_norm_to_unit_norm(self):
+        if self.low_precision and self.W_dec.is_cuda:
+            from vit_prisma.b200.sae_engine import unit_norm_rows_
+            masters = self._engine_params()
+            unit_norm_rows_(masters[1])                 # normalise the fp32 master, then round: ||row|| = 1 to bf16 precision
+            ops.cast_into(masters[1], self._canonical_params()[1])
+            return
+        super().set_decoder_norm_to_unit_norm()
+
     def step_engine(self, gemm_impl: int = L.GEMM_AUTO):
         """The step engine bound to this module's parameter storage (rebuilt if the storage moved): the fused sparse TopK
         pipeline, or ``SaeDenseStepEngine`` for ``activation_fn_str == "relu"`` (dense products + L1) and for
@@ -265,7 +309,7 @@ class StandardSparseAutoencoder(SparseAutoencoder):
         if act == "relu" and getattr(self.cfg, "lp_norm", 1) != 1:
             raise NotImplementedError("B200 dense training step: only lp_norm == 1 (the reference default) is built")
         dense = act == "relu" or bool(self.cfg.use_ghost_grads)
-        wt, wd, be, bd = self._canonical_params()
+        wt, wd, be, bd = self._engine_params()
         eng = self._engine
         if eng is not None and getattr(eng, "is_data_parallel", False) and eng._key[:4] == self._engine_key(gemm_impl, dense)[:4]:
             return eng                       # the peer-memory engine owns the parameter storage: never rebuilt behind the trainer's back
@@ -285,7 +329,7 @@ class StandardSparseAutoencoder(SparseAutoencoder):
 
     def _engine_key(self, gemm_impl: int, dense: bool):
         """Identity of the storage a step engine is bound to (+ the options that change which engine class serves it)."""
-        wt, wd, be, bd = self._canonical_params()
+        wt, wd, be, bd = self._engine_params()
         return (wt.data_ptr(), wd.data_ptr(), be.data_ptr(), bd.data_ptr(), gemm_impl, dense)
 
     def enable_data_parallel(self, group, gemm_impl: int = L.GEMM_AUTO):
@@ -295,11 +339,15 @@ class StandardSparseAutoencoder(SparseAutoencoder):
         from vit_prisma.b200.p2p import SaeDPEngine
         if self.cfg.activation_fn_str != "topk":
             raise NotImplementedError("the fused step engine covers activation_fn_str == 'topk'")
-        wt, wd, be, bd = self._canonical_params()
+        wt, wd, be, bd = self._engine_params()
         eng = SaeDPEngine(group, wt.contiguous(), wd, be, bd, k=self.cfg.activation_fn_kwargs["k"], normalize_activations=self._norm_mode,
                           max_grad_norm=self.cfg.max_grad_norm, gemm_impl=gemm_impl)
-        # the nn.Parameters become views of the shared buffers, so state_dict()/save_model() see what the kernels update
-        self.W_enc.data, self.W_dec.data, self.b_enc.data, self.b_dec.data = eng.W_encT.t(), eng.W_dec, eng.b_enc, eng.b_dec
+        if self.low_precision:
+            # the peer-visible fp32 buffers become the masters; the bf16 nn.Parameters keep their storage and are refreshed per step
+            self._masters = (eng.W_encT, eng.W_dec, eng.b_enc, eng.b_dec)
+        else:
+            # the nn.Parameters become views of the shared buffers, so state_dict()/save_model() see what the kernels update
+            self.W_enc.data, self.W_dec.data, self.b_enc.data, self.b_dec.data = eng.W_encT.t(), eng.W_dec, eng.b_enc, eng.b_dec
         eng._key = self._engine_key(gemm_impl, False)
         eng._enc_version = self.W_enc._version
         self._engine = eng
@@ -314,32 +362,49 @@ class StandardSparseAutoencoder(SparseAutoencoder):
         from vit_prisma.b200.sae_engine import sae_prep
         return sae_prep(x2, torch.zeros_like(self.b_dec.data), self._norm_mode)
 
+    def _fire(self, hook: HookPoint, t: torch.Tensor) -> torch.Tensor:
+        """Fire a HookPoint.  Reduced-precision configs compute in fp32 on the master parameters; the hook sees (and may replace)
+        the tensor rounded to cfg.dtype -- the reference's own rounding points -- and the computation continues from what it returns."""
+        if not self.low_precision:
+            return hook(t)
+        return ops.cast(hook(ops.cast(t, self.dtype)), torch.float32)
+
+    def _compute_params(self):
+        """fp32 tensors the module-by-module route multiplies with: the parameters (float32 configs) or their masters."""
+        if self.low_precision and self.W_dec.is_cuda:
+            return self._engine_params()
+        return self._canonical_params()
+
+    def _out(self, t: torch.Tensor) -> torch.Tensor:
+        return ops.cast(t, self.dtype) if t.dtype != self.dtype else t
+
     def encode(self, x: torch.Tensor, return_hidden_pre: bool = False):
         from vit_prisma.b200.sae_engine import sae_prep
-        x = ops.cast(x, self.dtype) if x.dtype != self.dtype else x
+        x = ops.cast(x.contiguous(), torch.float32)
         lead = x.shape[:-1]
         x2 = x.reshape(-1, self.d_in).contiguous()
-        wt, wd, be, bd = self._canonical_params()
+        wt, wd, be, bd = self._compute_params()
         sae_in2, mu, sd = sae_prep(x2, bd, self._norm_mode)               # norm_in(x) - b_dec  (reference :560-566)
         self.ln_mu, self.ln_std = mu.view(*lead, 1), sd.view(*lead, 1)
-        sae_in = self.hook_sae_in(sae_in2.view(*lead, self.d_in))
+        sae_in = self._fire(self.hook_sae_in, sae_in2.view(*lead, self.d_in))
         hidden_pre, _ = ops.gemm(sae_in, wt, be)                           # sae_in @ W_enc + b_enc  (:568-574)
-        hidden_pre = self.hook_hidden_pre(hidden_pre)
-        feature_acts = self.hook_hidden_post(self.activation_fn(hidden_pre))
+        hidden_pre = self._fire(self.hook_hidden_pre, hidden_pre)
+        feature_acts = self._fire(self.hook_hidden_post, self.activation_fn(hidden_pre))
         if return_hidden_pre:
-            return sae_in, feature_acts, hidden_pre
-        return sae_in, feature_acts
+            return self._out(sae_in), self._out(feature_acts), self._out(hidden_pre)
+        return self._out(sae_in), self._out(feature_acts)
 
     def decode(self, features: torch.Tensor):
-        wt, wd, be, bd = self._canonical_params()
+        wt, wd, be, bd = self._compute_params()
+        features = ops.cast(features.contiguous(), torch.float32)
         wd_nk = wd.t().contiguous()                                        # [d_in, d_sae]: K-major operand of features @ W_dec
         out, _ = ops.gemm(features, wd_nk, bd)                             # (:584-592)
-        out = self.hook_sae_out(out)
+        out = self._fire(self.hook_sae_out, out)
         if self._norm_mode == "layer_norm":                                 # x * std + mu  (:89-90)
             out = ops.add(ops.mul(out, self.ln_std.expand_as(out)), self.ln_mu.expand_as(out))
         elif self._norm_mode == "constant_norm_rescale":
             out = ops.mul(out, self.ln_std.expand_as(out))
-        return out
+        return self._out(out)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -347,36 +412,36 @@ class StandardSparseAutoencoder(SparseAutoencoder):
         from vit_prisma.b200.sae_engine import sae_mse
         want_ghost = bool(self.cfg.use_ghost_grads) and self.training and dead_neuron_mask is not None   # (:609-614)
         lead = x.shape[:-1]
-        x32 = ops.cast(x, self.dtype) if x.dtype != self.dtype else x
+        x32 = ops.cast(x.contiguous(), torch.float32)             # reduced-precision configs: fp32 arithmetic on the master parameters
         x2 = x32.reshape(-1, self.d_in).contiguous()
-        sparse_ok = self.cfg.activation_fn_str == "topk" and not self._hooks_attached() and self.dtype == torch.float32
+        sparse_ok = self.cfg.activation_fn_str == "topk" and not self._hooks_attached()
         if sparse_ok:
             eng = self.step_engine()
             if eng._enc_version != self.W_enc._version:                    # parameters written outside the engine
                 eng.refresh_lo()
                 eng._enc_version = self.W_enc._version
             sae_out2, _idx, _val = eng.forward(x2)
-            sae_out = sae_out2.clone().view(*lead, self.d_in)
-            mse_loss = eng.scalars[3].clone()
+            sae_out = self._out(sae_out2.clone().view(*lead, self.d_in))
+            mse_loss = self._out(eng.scalars[3].clone())
             if getattr(self.cfg, "return_out_only", False):      # spliced into HookedSAEViT (reference :636-640)
                 # use_error_term: sae_out + (x - sae_out).detach() == x -- the clean activation flows on, the SAE's hooks still fired
                 return x if getattr(self, "use_error_term", False) else sae_out
-            feature_acts = eng.dense_feature_acts().view(*lead, self.d_sae)
+            feature_acts = self._out(eng.dense_feature_acts().view(*lead, self.d_sae))
             hidden_pre2 = eng.hidden_pre       # None on the fused encoder route (no dense pre-activations exist)
             if hidden_pre2 is None and want_ghost:
-                hidden_pre2, _ = ops.gemm(eng.sae_in, self._canonical_params()[0], self._canonical_params()[2])
+                hidden_pre2, _ = ops.gemm(eng.sae_in, self._compute_params()[0], self._compute_params()[2])
         else:
             _, feature_acts, _hidden_pre = self.encode(x32, return_hidden_pre=True)
             sae_out = self.decode(feature_acts)
             if getattr(self.cfg, "return_out_only", False):      # spliced into HookedSAEViT (reference :636-640)
                 # use_error_term: sae_out + (x - sae_out).detach() == x -- the clean activation flows on, the SAE's hooks still fired
                 return x if getattr(self, "use_error_term", False) else sae_out
-            mse_loss = sae_mse(x2, sae_out.reshape(-1, self.d_in).contiguous())
+            mse_loss = self._out(sae_mse(x2, ops.cast(sae_out.reshape(-1, self.d_in).contiguous(), torch.float32)))
             hidden_pre2 = _hidden_pre.reshape(-1, self.d_sae)
         ghost_loss = self.zero_loss.to(sae_out.device)
         if want_ghost:
             from vit_prisma.b200.sae_dense import ghost_loss_value
-            ghost_loss = ghost_loss_value(hidden_pre2.float().contiguous(), self._canonical_params()[1], x2.float(),
+            ghost_loss = ghost_loss_value(hidden_pre2.float().contiguous(), self._compute_params()[1], x2.float(),
                                           sae_out.reshape(-1, self.d_in).float().contiguous(), mse_loss.float(), dead_neuron_mask)
         if self.cfg.activation_fn_str != "topk":
             # sparsity = ||feature_acts||_p over dim 1, mean over dim 0 (reference :617; tiny reduction, host-side glue)

@@ -197,6 +197,8 @@ class VisionSAETrainer:
             scalars = engine.train_step_topk_ghost(sae_in, lr, n_forward_passes_since_fired, act_freq_scores, cfg.dead_feature_window)
         else:
             scalars = engine.train_step(sae_in, lr, since_fired=n_forward_passes_since_fired, act_freq=act_freq_scores)
+        if getattr(sparse_autoencoder, "low_precision", False):
+            sparse_autoencoder.export_masters()      # bf16 configs: the engine trained fp32 masters; refresh the module's parameters
         n_frac_active_tokens += sae_in.shape[0]
         # the engine's scalars buffer is rewritten by the next step: hand out copies (device-side, no host sync)
         mse_loss = scalars[3].clone()
