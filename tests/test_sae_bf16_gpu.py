@@ -4,7 +4,8 @@ Storage is what the reference's would be (bf16 nn.Parameters / state dict / acti
 the accumulated parameters are fp32 masters inside the step engine (the reference keeps bf16 only).  The fixture
 (tests/golden/make_golden_sae_bf16.py, unmodified reference + a one-entry dtype_mapping shim) holds two trajectories from the same
 bf16 initial state: the reference in bf16 and the reference in fp32.  Bars:
-  * step-0 reconstruction on identical bf16 weights: within 1e-2 of the reference's bf16 output (north_star bf16 bar);
+  * step-0 reconstruction on identical bf16 weights: one bf16 rounding from the reference's fp32 output, within 2e-2 (two bf16 ulps,
+    the bar the ViT tests use for tensors behind several rounded adds) of its bf16 output, and closer to fp32 than that is;
   * losses: within 1e-2 of the reference's bf16 run, within 1e-4 of its fp32 run (our arithmetic is the fp32 one);
   * parameters after every step: bf16 tensors, no further from the fp32 trajectory than one bf16 rounding (2^-8 relative), and never
     further from it than the reference's own bf16 run is.
@@ -29,8 +30,10 @@ def _trainer(gold):
                                          normalize_activations=gold["norm"], b_dec_init_method="zeros", lr=gold["lr"],
                                          lr_warm_up_steps=gold["warm_up_steps"], train_batch_size=gold["batch"], max_grad_norm=1.0,
                                          initialization_method="independent", log_to_wandb=False, n_checkpoints=0,
-                                         checkpoint_path="/tmp/prisma_b200_unused", num_epochs=1)
-    cfg.total_training_steps = gold["total_steps"]
+                                         checkpoint_path="/tmp/prisma_b200_unused",
+                                         # total_training_steps is derived: int(1.3e6 * num_epochs) images x context_size tokens // batch
+                                         num_epochs=(gold["total_steps"] + 0.5) / 1_300_000, context_size=gold["batch"])
+    assert cfg.total_training_steps == gold["total_steps"]
     trainer = VisionSAETrainer(cfg, model=None, dataset=None, activations_store=object())
     sae = trainer.sparse_coder
     sae.load_state_dict({k: v.cuda() for k, v in gold["init"].items()})
@@ -45,9 +48,16 @@ def test_bf16_sae_trains_on_fp32_masters_and_exports_bf16_parameters():
     B = gold["batch"]
     # step-0 reconstruction through the module's own forward (bf16 weights identical to the reference's)
     sae.eval()
+    sae.set_decoder_norm_to_unit_norm()                          # the reference's loop normalises before its first forward (train_sae.py:306)
     out0 = sae(data[:B])[0]
     assert out0.dtype == torch.bfloat16
-    assert rel_err(out0.float().cpu(), gold["steps"][0]["sae_out"].float()) <= 1e-2
+    e32 = rel_err(out0.float().cpu(), gold["steps_fp32"][0]["sae_out"])
+    e16 = rel_err(out0.float().cpu(), gold["steps"][0]["sae_out"].float())
+    r16 = rel_err(gold["steps"][0]["sae_out"].float(), gold["steps_fp32"][0]["sae_out"])
+    print(f"step-0 sae_out: ours vs fp32 run {e32:.2e}, ours vs bf16 run {e16:.2e}, bf16 run vs fp32 run {r16:.2e}")
+    assert e32 <= 2.0 ** -8          # fp32 arithmetic, one rounding of the output to bf16
+    assert e16 <= 2e-2               # the reference's bf16 output went through four bf16 roundings (decode, + b_dec, * std, + mu): two ulps
+    assert e32 <= r16 + 1e-3
     act_freq, since_fired, n_frac, opt, sched = trainer.initialize_training_variables()
     for s, (rec16, rec32) in enumerate(zip(gold["steps"], gold["steps_fp32"])):
         x = data[s * B:(s + 1) * B].unsqueeze(1)
