@@ -4,8 +4,8 @@ Storage is what the reference's would be (bf16 nn.Parameters / state dict / acti
 the accumulated parameters are fp32 masters inside the step engine (the reference keeps bf16 only).  The fixture
 (tests/golden/make_golden_sae_bf16.py, unmodified reference + a one-entry dtype_mapping shim) holds two trajectories from the same
 bf16 initial state: the reference in bf16 and the reference in fp32.  Bars:
-  * step-0 reconstruction on identical bf16 weights: one bf16 rounding from the reference's fp32 output, within 2e-2 (two bf16 ulps,
-    the bar the ViT tests use for tensors behind several rounded adds) of its bf16 output, and closer to fp32 than that is;
+  * step-0 reconstruction on identical bf16 weights: one bf16 rounding from the reference's fp32 output; its bf16 output is itself
+    8e-2 from that (bf16 ties change the TopK support), so against it the bar is the triangle inequality, not 1e-2;
   * losses: within 1e-2 of the reference's bf16 run, within 1e-4 of its fp32 run (our arithmetic is the fp32 one);
   * parameters after every step: bf16 tensors, no further from the fp32 trajectory than one bf16 rounding (2^-8 relative), and never
     further from it than the reference's own bf16 run is.
@@ -56,7 +56,11 @@ def test_bf16_sae_trains_on_fp32_masters_and_exports_bf16_parameters():
     r16 = rel_err(gold["steps"][0]["sae_out"].float(), gold["steps_fp32"][0]["sae_out"])
     print(f"step-0 sae_out: ours vs fp32 run {e32:.2e}, ours vs bf16 run {e16:.2e}, bf16 run vs fp32 run {r16:.2e}")
     assert e32 <= 2.0 ** -8          # fp32 arithmetic, one rounding of the output to bf16
-    assert e16 <= 2e-2               # the reference's bf16 output went through four bf16 roundings (decode, + b_dec, * std, + mu): two ulps
+    # The reference's OWN bf16 output is 8e-2 (max-norm) from its fp32 output on this fixture: hidden_pre rounded to bf16 ties and
+    # reorders pre-activations near the k-th, so its TopK support differs from the exact one on some rows and whole features come
+    # or go.  No implementation can be within 1e-2 of that output AND of the truth; the bars are therefore: one bf16 rounding from
+    # the fp32 run (above), no further from the bf16 run than the bf16 run is from fp32 (triangle), closer to fp32 than it is.
+    assert e16 <= r16 + e32 + 1e-3
     assert e32 <= r16 + 1e-3
     act_freq, since_fired, n_frac, opt, sched = trainer.initialize_training_variables()
     for s, (rec16, rec32) in enumerate(zip(gold["steps"], gold["steps_fp32"])):

@@ -388,4 +388,5 @@ class SaeDPEngine(SaeStepEngine):
             g.barrier(ps)
         return [("p2p barrier + reduce-scatter (peer loads over NVLink)", rs, dict(nvlink_bytes=link, ncu=r"k_p2p_reduce_scatter")),
                 ("p2p barrier + sharded Adam + all-gather (peer stores) + barrier", adam,
-                 dict(bytes=60 * self.d * self.F // n, nvlink_bytes=(n - 1) / n * 12 * self.d * self.F, ncu=r"k_p2p_adam_allgather"))]
+                 dict(bytes=60 * self.d * self.F // n, nvlink_bytes=(n - 1) / n * (8 if self.W_encT_lo is None else 12) * self.d * self.F,
+                      ncu=r"k_p2p_adam_allgather"))]     # pushed per rank: its W_dec and W_encT rows (+ the tf32 residual plane of the dense encoder) to N-1 peers
