@@ -17,11 +17,69 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
+def bf16_trainer(rank, world, dev):
+    """DP_MODE=bf16_trainer: the cfg #5 class through VisionSAETrainer(p2p_group=...) -- bf16 module storage, fp32 masters living in
+    the peer-visible buffers, parameters exported after every step (after the deferred W_dec all-gather has landed).  Every rank
+    takes 1/N of each batch of tests/golden/sae_bf16_v.pt; the result must be the reference's fp32 trajectory rounded to bf16."""
+    import contextlib
+    import io
+    from tests.util import load_golden
+    from vit_prisma.b200.p2p import P2PGroup
+    from vit_prisma.sae.config import VisionModelSAERunnerConfig
+    from vit_prisma.sae.train_sae import VisionSAETrainer
+    gold = load_golden("sae_bf16_v.pt")
+    B, per = gold["batch"], gold["batch"] // world
+    with contextlib.redirect_stdout(io.StringIO()):
+        cfg = VisionModelSAERunnerConfig(d_in=gold["d_in"], expansion_factor=gold["d_sae"] // gold["d_in"], activation_fn_str="topk",
+                                         activation_fn_kwargs={"k": gold["k"]}, _device=str(dev), _dtype="bfloat16",
+                                         normalize_activations=gold["norm"], b_dec_init_method="zeros", lr=gold["lr"],
+                                         lr_warm_up_steps=gold["warm_up_steps"], train_batch_size=per, max_grad_norm=1.0,
+                                         initialization_method="independent", log_to_wandb=False, n_checkpoints=0,
+                                         checkpoint_path="/tmp/prisma_b200_unused",
+                                         num_epochs=(gold["total_steps"] + 0.5) / 1_300_000, context_size=per)
+        trainer = VisionSAETrainer(cfg, model=None, dataset=None, activations_store=object(), p2p_group=P2PGroup(rank, world, dev))
+    assert cfg.total_training_steps == gold["total_steps"]
+    sae = trainer.sparse_coder
+    sae.load_state_dict({k: v.to(dev) for k, v in gold["init"].items()})
+    act_freq, since_fired, n_frac, opt, sched = trainer.initialize_training_variables()
+    trainer.enable_data_parallel_if_requested()
+    data = gold["data"].to(dev)
+    ok, worst = True, 0.0
+    for s, rec32 in enumerate(gold["steps_fp32"]):
+        x = data[s * B + rank * per: s * B + (rank + 1) * per].unsqueeze(1)
+        _, mse, _, _, act_freq, since_fired, n_frac = trainer.train_step(sae, opt, sched, act_freq, since_fired, n_frac, x, s, s * B)
+        m = mse.detach().float().reshape(1).clone()
+        dist.all_reduce(m)                                   # shares of the global mean add up
+        if abs(m.item() - rec32["mse"]) > 1e-4 * rec32["mse"]:
+            ok = False
+            print(f"[rank {rank}] step {s}: mse {m.item()} vs {rec32['mse']}", flush=True)
+        sd = sae.state_dict()
+        for name, ref in rec32["params_after"].items():
+            if name == "W_dec":
+                ref = ref / ref.norm(dim=1, keepdim=True)
+            mine = sd[name]
+            e = float((mine.float().cpu() - ref).abs().max()) / float(ref.abs().max())
+            worst = max(worst, e)
+            if mine.dtype != torch.bfloat16 or e > 2.0 ** -8 + 1e-6:
+                ok = False
+                print(f"[rank {rank}] step {s}: {name} {mine.dtype} {e:.2e} from the fp32 trajectory", flush=True)
+    return ok, worst, sae.step_engine().describe_exchange()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)          # handle exchange + test barriers only
+    if os.environ.get("DP_MODE") == "bf16_trainer":
+        ok, worst, exch = bf16_trainer(rank, world, dev)
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"DP_RESULT world={world} ok={bool(flag.item())} worst_param_rel_err={worst:.2e} (bf16 trainer) exchange: {exch}", flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if flag.item() == 1.0 else 1)
     from oracle.sae_oracle import lr_multiplier
     from tests.util import load_golden, rel_err
     from vit_prisma.b200.p2p import P2PGroup, SaeDPEngine
