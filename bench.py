@@ -252,7 +252,7 @@ def run_reference_arm(args):
     steps, warm = args.steps, args.warmup
     threads = _cpu_cores()
     torch.set_num_threads(threads)
-    if args.workload in ("all", "sae", "cfg5"):      # cfg5's reference leg is the headline SAE sample (the oracle is fp32, d_sae 24576)
+    if args.workload in ("all", "sae", "cfg5", "sae_fwd"):      # cfg5 / sae_fwd's reference leg is the headline SAE sample (the oracle is fp32, d_sae 24576)
         from oracle.sae_oracle import sae_train_step
         batch = 1024   # bounded sample of the 4096-token step: the dense products are linear in the token count
         p, state, x = _cpu_sae_setup(batch)
@@ -663,6 +663,49 @@ def run_sae(args, ctx, spec=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def run_sae_forward(args, ctx, expansion=64):
+    """north_star's forward-only shape: SAE encoder -> TopK -> decoder at d_model 768, dict 768 x 64, 4096 tokens per call,
+    against SURVEY 8(d)'s forward bytes `4*(2*Bt*d) + 4*d*F + 4*F + 4*d*min(F, Bt*k)` (sparse outputs; no dense feature_acts).
+    Every rank runs its own replica (no collective); the record reports the sum."""
+    from vit_prisma.b200.sae_engine import SaeStepEngine, unit_norm_rows_
+    from vit_prisma.b200.synthetic import activation_pool, sae_init_params
+    d, k, Bt = SAE_CFG["d_in"], SAE_CFG["k"], SAE_CFG["batch"]
+    F = d * expansion
+    p = sae_init_params(d, F, device=ctx.dev)
+    eng = SaeStepEngine(p["W_encT"], p["W_dec"], p["b_enc"], p["b_dec"], k=k, normalize_activations="layer_norm")
+    unit_norm_rows_(eng.W_dec)
+    eng.refresh_lo()
+    pool = activation_pool(Bt * 8, d, seed=ctx.rank).to(ctx.dev)
+    n = max(args.steps, 10)
+    for i in range(max(args.warmup, 3)):
+        eng.forward(pool[(i % 8) * Bt:(i % 8 + 1) * Bt])
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        eng.forward(pool[(i % 8) * Bt:(i % 8 + 1) * Bt])
+    e1.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / n
+    if ctx.rank != 0:
+        return None
+    peaks = _peaks()
+    fwd_bytes = 4 * (2 * Bt * d) + 4 * d * F + 4 * F + 4 * d * min(F, Bt * k)
+    gbs = fwd_bytes / (ms / 1e3) / 1e9
+    tf32_peak = peaks["bf16_tflops"] / 2
+    return {"metric": f"SAE forward tokens/sec (encoder -> TopK -> decoder, d_model={d}, dict={d}x{expansion}, k={k})",
+            "value": ctx.world * Bt / (ms / 1e3), "unit": "tokens/s", "ms_per_call": ms, "n_gpus": ctx.world, "calls": n,
+            "config": {"workload": "sae_forward_north_star_shape", "api": "SaeStepEngine.forward (sparse idx / val + reconstruction)",
+                       "d_in": d, "d_sae": F, "k": k, "tokens_per_call": Bt, "encoder": eng.describe_encoder()},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "algorithmic_bytes": fwd_bytes,
+                         "note": "the candidate GEMM is one TF32 tensor-core pass (fp32-exact TopK indices against the reference need at "
+                                 "least that): the call is tensor-bound, not HBM-bound",
+                         "encoder_tf32_frac": 2.0 * Bt * F * d / (ms / 1e3) / 1e12 / tf32_peak,
+                         "tf32_peak_tflops": tf32_peak, "tf32_peak_source": "bf16 burst peak of MEASURED_PEAKS.json / 2"}}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def run_cfg4(args, ctx):
     """BASELINE.json configs[3]: CLIP ViT-L/14 run_with_cache feeding an SAE (d_model 1024, dict 1024 x 64, TopK 32), data parallel:
     every rank runs its own VisionActivationsStore over its own synthetic image shard (names_filter = one resid_post,
@@ -817,7 +860,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "sae", "vit", "cfg4", "cfg5"],
+    ap.add_argument("--workload", default="all", choices=["all", "sae", "vit", "cfg4", "cfg5", "sae_fwd"],
                     help="all (default) = SAE training step as the headline record + the full run_with_cache record under 'secondary'")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="ViT model dtype (the SAE step is fp32)")
     ap.add_argument("--batch", type=int, default=512, help="ViT images per step per GPU")
@@ -837,6 +880,8 @@ def main():
             line = run_cfg4(args, ctx)
         if args.workload == "cfg5":
             line = run_sae(args, ctx, spec=SAE_CFG5)
+        if args.workload == "sae_fwd":
+            line = run_sae_forward(args, ctx)
         if args.workload in ("all", "sae"):
             line = run_sae(args, ctx)
             if ctx.world > 1:
@@ -844,6 +889,9 @@ def main():
                 if line is not None:
                     line["dp_parity"], line["dp_parity_detail"] = ok, detail
                 rc = 0 if ok else 3
+            fwd = run_sae_forward(args, ctx)              # north_star's forward-only shape (dict 768 x 64), nested
+            if line is not None and fwd is not None:
+                line["forward_north_star"] = fwd
         if args.workload in ("all", "vit"):
             vargs = argparse.Namespace(**vars(args))
             if args.workload == "all":
