@@ -63,7 +63,21 @@ def bf16_trainer(rank, world, dev):
             if mine.dtype != torch.bfloat16 or e > 2.0 ** -8 + 1e-6:
                 ok = False
                 print(f"[rank {rank}] step {s}: {name} {mine.dtype} {e:.2e} from the fp32 trajectory", flush=True)
-    return ok, worst, sae.step_engine().describe_exchange()
+    from vit_prisma.b200.p2p import SaeDPEngine
+    eng = sae.step_engine()
+    if not isinstance(eng, SaeDPEngine):                     # the trainer must keep the peer-memory engine (round-1 advisor finding)
+        ok = False
+        print(f"[rank {rank}] trainer runs on {type(eng).__name__}, not SaeDPEngine", flush=True)
+    # identical parameters on every rank: compare an order-sensitive checksum of the fp32 masters with rank 0's
+    eng.wait_parameters()
+    sums = torch.stack([(t.double() * torch.arange(1, t.numel() + 1, device=dev, dtype=torch.float64).reshape(t.shape)).sum()
+                        for t in (eng.W_encT, eng.W_dec, eng.b_enc, eng.b_dec)])
+    ref = sums.clone()
+    dist.broadcast(ref, src=0)
+    if not torch.equal(sums, ref):
+        ok = False
+        print(f"[rank {rank}] parameters differ from rank 0's: {sums.tolist()} vs {ref.tolist()}", flush=True)
+    return ok, worst, eng.describe_exchange()
 
 
 def main():
