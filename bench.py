@@ -687,6 +687,20 @@ def run_sae_forward(args, ctx, expansion=64):
     e1.record()
     ctx.barrier()
     ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / n
+    fb_rows, rescored = eng.fallback_rows(), eng.rescored_per_row(Bt)
+
+    def phase_ms(bits, reps=5):                       # one phase of the fused encode alone, warm replays
+        import ctypes
+        from vit_prisma.b200 import _lib as L
+        lib, st = L.get_lib(), torch.cuda.current_stream().cuda_stream
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            L.check(lib.pb_sae_encode_topk_fused(ctypes.byref(eng._enc_desc(Bt, bits)), st), "pb_sae_encode_topk_fused")
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    phases = {"candidate_gemm_ms": phase_ms(1), "select_rescore_ms": phase_ms(2), "exact_path_ms": phase_ms(4)}
     if ctx.rank != 0:
         return None
     peaks = _peaks()
@@ -697,6 +711,7 @@ def run_sae_forward(args, ctx, expansion=64):
             "value": ctx.world * Bt / (ms / 1e3), "unit": "tokens/s", "ms_per_call": ms, "n_gpus": ctx.world, "calls": n,
             "config": {"workload": "sae_forward_north_star_shape", "api": "SaeStepEngine.forward (sparse idx / val + reconstruction)",
                        "d_in": d, "d_sae": F, "k": k, "tokens_per_call": Bt, "encoder": eng.describe_encoder()},
+            "phases": phases, "exact_path_rows_last_call": fb_rows, "rescored_per_row": rescored,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                          "algorithmic_bytes": fwd_bytes,
                          "note": "the candidate GEMM is one TF32 tensor-core pass (fp32-exact TopK indices against the reference need at "
@@ -889,7 +904,10 @@ def main():
                 if line is not None:
                     line["dp_parity"], line["dp_parity_detail"] = ok, detail
                 rc = 0 if ok else 3
-            fwd = run_sae_forward(args, ctx)              # north_star's forward-only shape (dict 768 x 64), nested
+            try:                                           # north_star's forward-only shape (dict 768 x 64), nested; never costs the headline
+                fwd = run_sae_forward(args, ctx)
+            except Exception as e:                         # noqa: BLE001 -- reported in the line, not swallowed
+                fwd = {"error": f"{type(e).__name__}: {e}"}
             if line is not None and fwd is not None:
                 line["forward_north_star"] = fwd
         if args.workload in ("all", "vit"):

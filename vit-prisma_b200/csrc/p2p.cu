@@ -115,6 +115,21 @@ __global__ void k_p2p_sum_small(P2PTables t, float* __restrict__ out, int which,
   }
 }
 
+// gb_enc [F], gb_dec [d], fired [F] summed over ranks in one launch (three launches of k_p2p_sum_small + a memset before:
+// four dependent ~4 us launches in front of the reduce-scatter); thread 0 also resets the step's accumulators
+__global__ void __launch_bounds__(256) k_p2p_sum_small3(P2PTables t, float* __restrict__ gb_enc_red, float* __restrict__ gb_dec_red,
+                                                       float* __restrict__ fired_red, int F, int d, float* __restrict__ part_accum) {
+  if (blockIdx.x == 0 && threadIdx.x < 4) part_accum[threadIdx.x] = 0.f;   // [0] gradient-norm partial, [1..2] encoder row-norm maxima of the owned slice
+  const int n = 2 * F + d;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int which = i < F ? 0 : i < 2 * F ? 1 : 2;
+    const int j = which == 0 ? i : which == 1 ? i - F : i - 2 * F;
+    float acc = 0.f;
+    for (int r = 0; r < t.world; ++r) acc += (which == 0 ? t.gb_enc[r] : which == 1 ? t.fired[r] : t.gb_dec[r])[j];
+    (which == 0 ? gb_enc_red : which == 1 ? fired_red : gb_dec_red)[j] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------- reduce-scatter + norm
 // rows [f0, f1) of both gradient matrices: own += sum of peers; partial ||g||^2 -> every peer's norm_parts[rank]
 // One gradient array's owned slice: own[i] = sum over ranks (rank order) of that rank's copy; returns this thread's share of ||.||^2.
@@ -349,13 +364,6 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
 }
 
 // norm_parts layout on every rank: [0, 8) gradient-norm partials, [8, 16) max ||w_f|| partials, [16, 24) max ||w_f - trunc(w_f)|| partials
-__global__ void k_p2p_publish_wmax(P2PTables t, const float* __restrict__ wmax_accum) {
-  const int r = threadIdx.x;
-  if (r < t.world) {
-    t.norm_parts[r][PB_MAX_RANKS + t.rank] = wmax_accum[0];          // peer stores
-    t.norm_parts[r][2 * PB_MAX_RANKS + t.rank] = wmax_accum[1];
-  }
-}
 __global__ void k_p2p_wmax_reduce(P2PTables t, float* __restrict__ enc_norm_max) {
   float a = 0.f, b = 0.f;
   for (int r = 0; r < t.world; ++r) {
@@ -367,10 +375,15 @@ __global__ void k_p2p_wmax_reduce(P2PTables t, float* __restrict__ enc_norm_max)
 }
 
 // replicated tiny updates: b_dec Adam (identical inputs on every rank -> identical result) and the dead-feature counters
-__global__ void __launch_bounds__(256) k_p2p_small_updates(float* __restrict__ b_dec, const float* __restrict__ gb_dec_red, float* __restrict__ m_bd,
+__global__ void __launch_bounds__(256) k_p2p_small_updates(P2PTables t, const float* __restrict__ wmax_accum, float* __restrict__ b_dec,
+                                                          const float* __restrict__ gb_dec_red, float* __restrict__ m_bd,
                                                           float* __restrict__ v_bd, const float* __restrict__ fired_red,
                                                           float* __restrict__ since_fired, float* __restrict__ act_freq,
                                                           const SaeScalarsP2P* __restrict__ sc, AdamHyperP2P h, int d, int F) {
+  if (blockIdx.x == 0 && threadIdx.x < t.world) {      // publish this rank's encoder row-norm maxima to every peer (was its own launch)
+    t.norm_parts[threadIdx.x][PB_MAX_RANKS + t.rank] = wmax_accum[0];
+    t.norm_parts[threadIdx.x][2 * PB_MAX_RANKS + t.rank] = wmax_accum[1];
+  }
   const float clip = sc->clip_coef;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x) {
     if (i < d) {
@@ -421,13 +434,8 @@ extern "C" int pb_p2p_reduce_scatter(const PbP2PStep* s, pb_stream_t stream) {
   PB_CHECK_ARG((s->F % s->world) == 0 && (((int64_t)(s->F / s->world) * s->d) % 4) == 0, "pb_p2p_reduce_scatter: F must divide evenly by world");
   cudaStream_t st = (cudaStream_t)stream;
   const int per = s->F / s->world, f0 = s->rank * per, f1 = f0 + per;
-  k_p2p_sum_small<<<(s->F + 255) / 256, 256, 0, st>>>(t, s->gb_enc_red, 1, s->F);
+  k_p2p_sum_small3<<<(2 * s->F + s->d + 255) / 256, 256, 0, st>>>(t, s->gb_enc_red, s->gb_dec_red, s->fired_red, s->F, s->d, s->part_accum);
   PB_LAUNCH_CHECK();
-  k_p2p_sum_small<<<(s->d + 255) / 256, 256, 0, st>>>(t, s->gb_dec_red, 2, s->d);
-  PB_LAUNCH_CHECK();
-  k_p2p_sum_small<<<(s->F + 255) / 256, 256, 0, st>>>(t, s->fired_red, 3, s->F);
-  PB_LAUNCH_CHECK();
-  PB_CUDA(cudaMemsetAsync(s->part_accum, 0, 4 * sizeof(float), st));   // [0] gradient-norm partial, [1..2] encoder row-norm maxima of the owned slice
   PB_CHECK_ARG(!s->mc_gW_dec == !s->mc_gW_encT, "pb_p2p_reduce_scatter: both multicast gradient views or none");
   k_p2p_reduce_scatter<<<pb_sm_count() * 4, 256, 0, st>>>(t, f0, f1, s->d, s->gb_enc_red, s->gb_dec_red, s->F, s->part_accum, s->mc_gW_dec,
                                                           s->mc_gW_encT);
@@ -467,10 +475,8 @@ extern "C" int pb_p2p_adam_allgather(const PbP2PStep* s, pb_stream_t stream) {
   else PB_P2P_ADAM(12);
 #undef PB_P2P_ADAM
   PB_LAUNCH_CHECK();
-  k_p2p_publish_wmax<<<1, 32, 0, st>>>(t, s->part_accum + 1);
-  PB_LAUNCH_CHECK();
-  k_p2p_small_updates<<<(s->F + 255) / 256, 256, 0, st>>>(s->b_dec, s->gb_dec_red, s->m_bd, s->v_bd, s->fired_red, s->since_fired, s->act_freq,
-                                                        (const SaeScalarsP2P*)s->scalars, h, d, s->F);
+  k_p2p_small_updates<<<(s->F + 255) / 256, 256, 0, st>>>(t, s->part_accum + 1, s->b_dec, s->gb_dec_red, s->m_bd, s->v_bd, s->fired_red, s->since_fired,
+                                                        s->act_freq, (const SaeScalarsP2P*)s->scalars, h, d, s->F);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -355,7 +355,11 @@ class SaeDPEngine(SaeStepEngine):
         g.barrier(ps)                                   # norm partials published; all peer reads of this step are done
         ps.defer_dec = 1 if self.overlap_dec else 0
         L.check(lib.pb_p2p_adam_allgather(C.byref(ps), st), "pb_p2p_adam_allgather")
-        if self.overlap_dec:                            # W_dec rows -> peers on the side stream, with its own barrier
+        g.barrier(ps)                                   # every rank holds the updated encoder (and, without overlap, decoder) parameters
+        if self.overlap_dec:
+            # W_dec rows -> peers on the side stream with its own flag set, started AFTER the encoder all-gather has completed everywhere:
+            # started together with it (run 13) the two pushes shared the egress links and the barrier above waited for both -- no gain.
+            # From here the traffic runs under the next step's prep / candidate GEMM / select and is awaited at its decode.
             self._ev_adam.record(torch.cuda.current_stream())
             self._side.wait_event(self._ev_adam)
             side = self._side.cuda_stream
@@ -363,7 +367,6 @@ class SaeDPEngine(SaeStepEngine):
             g.barrier2(ps, side)
             self._ev_dec = torch.cuda.Event()
             self._ev_dec.record(self._side)
-        g.barrier(ps)                                   # every rank holds the updated encoder (and, without overlap, decoder) parameters
         if self.encoder == "fused":                     # error bound of the next step's tf32 pass: largest encoder-column norms, merged over ranks
             L.check(lib.pb_p2p_wmax(C.byref(ps), self.enc_norm_max.data_ptr(), st), "pb_p2p_wmax")
         return self.scalars
