@@ -91,3 +91,29 @@ def test_bf16_sae_trains_on_fp32_masters_and_exports_bf16_parameters():
     sae.load_state_dict({k: v.cuda() for k, v in gold["init"].items()})
     eng2 = sae.step_engine()
     assert torch.equal(eng2.W_dec.cpu(), gold["init"]["W_dec"].float())
+
+
+def test_bf16_module_routes_agree_and_hooks_see_bf16():
+    """A bf16 module computes in fp32 on its masters on BOTH routes: the sparse engine route (no hooks) and the module-by-module route
+    (a HookPoint is live).  Hooks see tensors rounded to cfg.dtype -- the reference's rounding points -- and the two routes agree to
+    bf16 rounding; encode / decode return cfg.dtype like the reference's do."""
+    gold = load_golden("sae_bf16_v.pt")
+    cfg, trainer, sae = _trainer(gold)
+    sae.eval()
+    x = gold["data"][:gold["batch"]].cuda()
+    out_sparse = sae(x)
+    seen = {}
+    def grab(t, hook):
+        seen[hook.name] = (t.dtype, tuple(t.shape))
+        return None
+    out_hooked = sae.run_with_hooks(x, fwd_hooks=[("hook_hidden_pre", grab), ("hook_sae_out", grab)])
+    assert seen["hook_hidden_pre"] == (torch.bfloat16, (gold["batch"], gold["d_sae"]))
+    assert seen["hook_sae_out"][0] == torch.bfloat16
+    assert out_hooked[0].dtype == torch.bfloat16 and out_sparse[0].dtype == torch.bfloat16
+    # the hooked route rounds sae_in / hidden_pre / feature_acts / sae_out to bf16 on the way (as the reference does): two bf16 ulps
+    assert rel_err(out_hooked[0].float(), out_sparse[0].float()) <= 2e-2
+    assert abs(out_hooked[3].item() - out_sparse[3].item()) <= 2e-2 * abs(out_sparse[3].item())
+    sae_in, feats = sae.encode(x)
+    assert sae_in.dtype == torch.bfloat16 and feats.dtype == torch.bfloat16 and feats.shape == (gold["batch"], gold["d_sae"])
+    assert int((feats > 0).sum(dim=1).max()) <= gold["k"]
+    assert sae.decode(feats).dtype == torch.bfloat16

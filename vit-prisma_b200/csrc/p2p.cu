@@ -137,9 +137,14 @@ __global__ void __launch_bounds__(256) k_p2p_sum_small3(P2PTables t, float* __re
 template <int W, int U>
 __device__ __forceinline__ float rs_peer_slice(const P2PTables& t, int m, int64_t base4, int64_t n4, float4* __restrict__ own, int64_t tid,
                                                int64_t stride) {
+  // slot j holds rank (t.rank + j) % world: at any instant the 8 GPUs pull from 8 different peers (a permutation through the
+  // switch) instead of all hitting rank 0, then rank 1, ...; the sum therefore runs owner-first, in the same order every step
   const float4* src[W];
 #pragma unroll
-  for (int r = 0; r < W; ++r) src[r] = r < t.world ? reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4 : nullptr;
+  for (int j = 0; j < W; ++j) {
+    const int r = (t.rank + j) % t.world;
+    src[j] = j < t.world ? reinterpret_cast<const float4*>(m == 0 ? t.gW_dec[r] : t.gW_encT[r]) + base4 : nullptr;
+  }
   float nsq = 0.f;
   int64_t i = tid;
   for (; i + (U - 1) * stride < n4; i += U * stride) {
@@ -170,9 +175,12 @@ __device__ __forceinline__ float rs_peer_slice(const P2PTables& t, int m, int64_
   return nsq;
 }
 
-__global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PTables t, int f0, int f1, int d, const float* __restrict__ gb_enc_red,
-                                                           const float* __restrict__ gb_dec_red, int F, float* __restrict__ part_accum,
-                                                           const float* __restrict__ mc_gW_dec, const float* __restrict__ mc_gW_encT) {
+// W / U: compile-time rank count and elements per trip of the peer-load path (0 / 0 = the multicast path).  One instantiation per
+// case: as one kernel with a runtime switch the four unrolled bodies cost 254 registers (one CTA per SM).
+template <int W, int U>
+__global__ void __launch_bounds__(256, 3) k_p2p_reduce_scatter(P2PTables t, int f0, int f1, int d, const float* __restrict__ gb_enc_red,
+                                                              const float* __restrict__ gb_dec_red, int F, float* __restrict__ part_accum,
+                                                              const float* __restrict__ mc_gW_dec, const float* __restrict__ mc_gW_encT) {
   const int64_t n4 = (int64_t)(f1 - f0) * d / 4;
   const int64_t base4 = (int64_t)f0 * d / 4;
   float nsq = 0.f;
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PTables t, int f0,
   for (int m = 0; m < 2; ++m) {
     float4* own = reinterpret_cast<float4*>(m == 0 ? t.gW_dec[t.rank] : t.gW_encT[t.rank]) + base4;
     const float* mc = m == 0 ? mc_gW_dec : mc_gW_encT;
-    if (mc) {
+    if constexpr (W == 0) {
       // summed inside the switch: this slice crosses NVLink once.  A multimem load is a round trip through the switch (several
       // microseconds): four independent loads per thread keep enough bytes in flight (one per trip ran at 270 GB/s, r2d_bench2).
       const float* src = mc + 4 * base4;
@@ -201,12 +209,8 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_scatter(P2PTables t, int f0,
     }
     // peer loads (NVLink): a load from a peer is a ~2 us round trip, so eight 16-byte loads per thread are issued before the first
     // is consumed -- all ranks' copies of U = 8 / world consecutive elements (adding them one by one inside a runtime-bounded
-    // loop ran at 489 GB/s at 8 ranks, r2g_bench8_peer; one element per trip at 2 ranks at 409 GB/s, r2i_bench2).  The sum runs in
-    // rank order, starting from rank 0, on every rank -- the same association everywhere.
-    if (t.world == 2) nsq += rs_peer_slice<2, 4>(t, m, base4, n4, own, tid, stride);
-    else if (t.world == 4) nsq += rs_peer_slice<4, 2>(t, m, base4, n4, own, tid, stride);
-    else if (t.world == 8) nsq += rs_peer_slice<8, 1>(t, m, base4, n4, own, tid, stride);
-    else nsq += rs_peer_slice<PB_MAX_RANKS, 1>(t, m, base4, n4, own, tid, stride);
+    // loop ran at 489 GB/s at 8 ranks, r2g_bench8_peer; one element per trip at 2 ranks at 409 GB/s, r2i_bench2).
+    if constexpr (W != 0) nsq += rs_peer_slice<W, U>(t, m, base4, n4, own, tid, stride);
   }
   // small vectors are fully reduced on every rank; only rank 0 counts their norm so the global sum counts them once
   if (t.rank == 0) {
@@ -269,6 +273,13 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
   float* W_encT = t.W_encT[t.rank];
   const float* gWd = t.gW_dec[t.rank];
   const float* gWe = t.gW_encT[t.rank];
+  // destination j = rank (t.rank + j) % world: every GPU addresses a different peer at a time (permutation traffic through the switch)
+  float *wdec_rot[PB_MAX_RANKS], *wenc_rot[PB_MAX_RANKS], *wlo_rot[PB_MAX_RANKS];
+#pragma unroll
+  for (int j = 0; j < PB_MAX_RANKS; ++j) {
+    const int r = (t.rank + j) % t.world;
+    wdec_rot[j] = t.W_dec[r]; wenc_rot[j] = t.W_encT[r]; wlo_rot[j] = t.W_encT_lo[r];
+  }
   for (int f = f0 + blockIdx.x * nw + warp; f < f1; f += gridDim.x * nw) {
     const int64_t base = (int64_t)f * d;
     float w[CHUNKS][4], gq[CHUNKS][4];
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
         for (int q = 0; q < 4; ++q) w[i][q] = w[i][q] * inv_nrm;
         if (defer_dec) st4(W_dec + base + 4 * c4, w[i]);                                   // own copy only: pb_p2p_push_dec sends it later
         else if (mc_W_dec) mc_st4(mc_W_dec + base + 4 * c4, w[i]);                         // all-gather: one multicast store
-        else for (int r = 0; r < t.world; ++r) st4(t.W_dec[r] + base + 4 * c4, w[i]);      // all-gather: peer stores
+        else for (int j = 0; j < t.world; ++j) st4(wdec_rot[j] + base + 4 * c4, w[i]);     // all-gather: peer stores, own copy first
       }
     }
     float esq = 0.f, elo = 0.f;
@@ -338,9 +349,9 @@ __global__ void __launch_bounds__(256) k_p2p_adam_allgather(P2PTables t, int f0,
         if (mc_W_encT) {
           mc_st4(mc_W_encT + base + 4 * c4, p);
         } else {
-          for (int r = 0; r < t.world; ++r) {
-            st4(t.W_encT[r] + base + 4 * c4, p);
-            if (t.W_encT_lo[r]) st4(t.W_encT_lo[r] + base + 4 * c4, lo);     // tf32 residual plane: dense 3xTF32 encoder only
+          for (int j = 0; j < t.world; ++j) {
+            st4(wenc_rot[j] + base + 4 * c4, p);
+            if (wlo_rot[j]) st4(wlo_rot[j] + base + 4 * c4, lo);             // tf32 residual plane: dense 3xTF32 encoder only
           }
         }
       }
@@ -437,8 +448,13 @@ extern "C" int pb_p2p_reduce_scatter(const PbP2PStep* s, pb_stream_t stream) {
   k_p2p_sum_small3<<<(2 * s->F + s->d + 255) / 256, 256, 0, st>>>(t, s->gb_enc_red, s->gb_dec_red, s->fired_red, s->F, s->d, s->part_accum);
   PB_LAUNCH_CHECK();
   PB_CHECK_ARG(!s->mc_gW_dec == !s->mc_gW_encT, "pb_p2p_reduce_scatter: both multicast gradient views or none");
-  k_p2p_reduce_scatter<<<pb_sm_count() * 4, 256, 0, st>>>(t, f0, f1, s->d, s->gb_enc_red, s->gb_dec_red, s->F, s->part_accum, s->mc_gW_dec,
-                                                          s->mc_gW_encT);
+#define PB_RS(W_, U_) k_p2p_reduce_scatter<W_, U_><<<pb_sm_count() * 3, 256, 0, st>>>(t, f0, f1, s->d, s->gb_enc_red, s->gb_dec_red, s->F, s->part_accum, s->mc_gW_dec, s->mc_gW_encT)
+  if (s->mc_gW_dec) PB_RS(0, 0);
+  else if (s->world == 2) PB_RS(2, 4);
+  else if (s->world == 4) PB_RS(4, 2);
+  else if (s->world == 8) PB_RS(8, 1);
+  else PB_RS(PB_MAX_RANKS, 1);
+#undef PB_RS
   PB_LAUNCH_CHECK();
   k_p2p_publish_norm<<<1, 32, 0, st>>>(t, s->part_accum);
   PB_LAUNCH_CHECK();
@@ -492,8 +508,8 @@ __global__ void __launch_bounds__(256) k_p2p_push_dec(P2PTables t, int f0, int f
       const float w[4] = {v.x, v.y, v.z, v.w};
       mc_st4(mc_W_dec + 4 * (base4 + i), w);
     } else {
-      for (int r = 0; r < t.world; ++r)
-        if (r != t.rank) (reinterpret_cast<float4*>(t.W_dec[r]) + base4)[i] = v;
+      for (int j = 1; j < t.world; ++j)                                   // rotated: a different peer per GPU at any instant
+        (reinterpret_cast<float4*>(t.W_dec[(t.rank + j) % t.world]) + base4)[i] = v;
     }
   }
 }
