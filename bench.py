@@ -655,6 +655,7 @@ def run_sae(args, ctx, spec=None):
                                                       + eng.describe_exchange() + ")" if world > 1 else "")},
            "clocks": clocks.summary(), "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
            "final_loss": final_loss,
+           **({"dp_trace_ms": eng.trace_report()} if getattr(eng, "_trace", None) else {}),
            "e2e": {"value": tokens / (e2e_ms / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": Bt * d * pool_host.element_size(), "d2h_bytes_per_step": 4,
                    "ms_per_step": e2e_ms / args.steps, "host_enqueue_ms_per_step": e2e_host_ms,
                    "overlap": "H2D of step i+1 on a copy stream under step i (DevicePrefetcher, depth 2)"},

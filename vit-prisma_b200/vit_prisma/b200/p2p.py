@@ -10,6 +10,7 @@ slice -> all-gather (peer stores).  Single-GPU semantics are preserved: the loss
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -283,6 +284,8 @@ class SaeDPEngine(SaeStepEngine):
         # read by the next decode); PRISMA_P2P_OVERLAP=0 keeps the whole all-gather inside the Adam kernel
         self.overlap_dec = os.environ.get("PRISMA_P2P_OVERLAP", "1") != "0" and g.world > 1
         self._side = torch.cuda.Stream(device=dev) if self.overlap_dec else None
+        self._trace = [] if os.environ.get("PRISMA_P2P_TRACE", "0") == "1" else None      # per-step CUDA-event marks (trace_report)
+        self._trace_step = []
         self._ev_adam = torch.cuda.Event() if self.overlap_dec else None
         self._ev_dec = None                                   # recorded on the side stream once every peer's W_dec rows have landed
         g.connect()
@@ -324,6 +327,33 @@ class SaeDPEngine(SaeStepEngine):
         return (f"peer loads / stores over NVLink: {int((n - 1) / n * (2 * self.d * self.F * 4 * 2) / 1e6)} MB per GPU per step"
                 + (f" ({getattr(self.group, 'multicast_note', '')})" if getattr(self.group, "multicast_note", "") else ""))
 
+    # ------------------------------------------------------------------ PRISMA_P2P_TRACE=1: CUDA events at the phase boundaries of every step
+    def _mark(self, name: str, stream=None) -> None:
+        if self._trace is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        self._trace_step.append((name, ev))
+
+    def trace_report(self, skip: int = 5) -> dict:
+        """Mean milliseconds between consecutive marks of a step (main stream) and, for marks on the side stream, since the step's
+        first mark.  Synchronises."""
+        if not self._trace:
+            return {}
+        torch.cuda.synchronize()
+        steps = self._trace[skip:] or self._trace
+        out, n = {}, len(steps)
+        for marks in steps:
+            t0, prev = marks[0][1], marks[0][1]
+            for name, ev in marks[1:]:
+                if name.startswith("side:"):
+                    out[name + " (since step start)"] = out.get(name + " (since step start)", 0.0) + t0.elapsed_time(ev) / n
+                else:
+                    out[name] = out.get(name, 0.0) + prev.elapsed_time(ev) / n
+                    prev = ev
+            out["step total"] = out.get("step total", 0.0) + t0.elapsed_time(prev) / n
+        return {k: round(v, 4) for k, v in out.items()}
+
     @torch.no_grad()
     def train_step(self, x: torch.Tensor, lr: float, since_fired=None, act_freq=None, want_out: bool = False) -> torch.Tensor:
         lib, st, g = L.get_lib(), _stream(), self.group
@@ -333,6 +363,10 @@ class SaeDPEngine(SaeStepEngine):
             raise L.PrismaB200Error(f"SaeDPEngine: every step (and every rank) must bring the same number of rows (had {self._dp_rows}, got {rows}); "
                                     "drop or pad short batches before the data-parallel step")
         self._dp_rows = rows
+        if self._trace is not None:
+            self._trace_step = []
+            self._trace.append(self._trace_step)
+        self._mark("start")
         # prep writes THIS rank's column sums of x into the shared xsum; decode needs the GLOBAL sums
         self._ensure_rows(rows)
         self.step_count += 1
@@ -342,20 +376,30 @@ class SaeDPEngine(SaeStepEngine):
         xsum_global, self.xsum = self.xsum, self.xsum_local
         self.encode_topk(x, pre_zeroed=True)
         self.xsum = xsum_global
+        self._mark("reset + prep + encode + topk")
         ps = self._p2p_desc(rows, float(lr), since_fired, act_freq)
         g.barrier(ps)
         L.check(lib.pb_p2p_sum_xsum(C.byref(ps), self.xsum.data_ptr(), st), "pb_p2p_sum_xsum")
+        self._mark("barrier + xsum")
         if self._ev_dec is not None:                    # the previous step's W_dec rows from every peer (side stream) must have landed
             torch.cuda.current_stream().wait_event(self._ev_dec)
             self._ev_dec = None
+            self._mark("wait for the deferred W_dec rows")
         L.check(lib.pb_sae_decode(C.byref(s), st), "pb_sae_decode")
+        self._mark("decode")
         L.check(lib.pb_sae_backward(C.byref(s), st), "pb_sae_backward")
+        self._mark("backward")
         g.barrier(ps)                                   # every rank's local gradients are complete
+        self._mark("barrier (gradients complete)")
         L.check(lib.pb_p2p_reduce_scatter(C.byref(ps), st), "pb_p2p_reduce_scatter")
+        self._mark("reduce-scatter")
         g.barrier(ps)                                   # norm partials published; all peer reads of this step are done
+        self._mark("barrier (norm parts)")
         ps.defer_dec = 1 if self.overlap_dec else 0
         L.check(lib.pb_p2p_adam_allgather(C.byref(ps), st), "pb_p2p_adam_allgather")
+        self._mark("sharded Adam + all-gather")
         g.barrier(ps)                                   # every rank holds the updated encoder (and, without overlap, decoder) parameters
+        self._mark("barrier (parameters)")
         if self.overlap_dec:
             # W_dec rows -> peers on the side stream with its own flag set, started AFTER the encoder all-gather has completed everywhere:
             # started together with it (run 13) the two pushes shared the egress links and the barrier above waited for both -- no gain.
@@ -363,12 +407,16 @@ class SaeDPEngine(SaeStepEngine):
             self._ev_adam.record(torch.cuda.current_stream())
             self._side.wait_event(self._ev_adam)
             side = self._side.cuda_stream
+            self._mark("side: push start", self._side)
             L.check(lib.pb_p2p_push_dec(C.byref(ps), side), "pb_p2p_push_dec")
+            self._mark("side: push done", self._side)
             g.barrier2(ps, side)
+            self._mark("side: barrier2 done", self._side)
             self._ev_dec = torch.cuda.Event()
             self._ev_dec.record(self._side)
         if self.encoder == "fused":                     # error bound of the next step's tf32 pass: largest encoder-column norms, merged over ranks
             L.check(lib.pb_p2p_wmax(C.byref(ps), self.enc_norm_max.data_ptr(), st), "pb_p2p_wmax")
+        self._mark("wmax")
         return self.scalars
 
     # ------------------------------------------------------------------ instrumentation: COLLECTIVE (every rank must call it)
