@@ -713,6 +713,9 @@ def run_sae_forward(args, ctx, expansion=64):
             "config": {"workload": "sae_forward_north_star_shape", "api": "SaeStepEngine.forward (sparse idx / val + reconstruction)",
                        "d_in": d, "d_sae": F, "k": k, "tokens_per_call": Bt, "encoder": eng.describe_encoder()},
             "phases": phases, "exact_path_rows_last_call": fb_rows, "rescored_per_row": rescored,
+            "caveat": "ms_per_call is the whole SaeStepEngine.forward call (prep + fused encode + decode + two fills); on the round-2 boxes it "
+                      "measured ~3x the sum of its phases replayed alone (1.84 vs 0.61 ms) and the difference was not diagnosed before the "
+                      "round's GPU minutes ran out -- read the phases for the kernels, the call figure as an upper bound",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                          "algorithmic_bytes": fwd_bytes,
                          "note": "the candidate GEMM is one TF32 tensor-core pass (fp32-exact TopK indices against the reference need at "

@@ -93,6 +93,7 @@ def test_bf16_sae_trains_on_fp32_masters_and_exports_bf16_parameters():
     assert torch.equal(eng2.W_dec.cpu(), gold["init"]["W_dec"].float())
 
 
+@pytest.mark.skip(reason="written after the round's GPU minutes were spent: never run on hardware, so it cannot vouch for anything yet")
 def test_bf16_module_routes_agree_and_hooks_see_bf16():
     """A bf16 module computes in fp32 on its masters on BOTH routes: the sparse engine route (no hooks) and the module-by-module route
     (a HookPoint is live).  Hooks see tensors rounded to cfg.dtype -- the reference's rounding points -- and the two routes agree to
@@ -110,9 +111,10 @@ def test_bf16_module_routes_agree_and_hooks_see_bf16():
     assert seen["hook_hidden_pre"] == (torch.bfloat16, (gold["batch"], gold["d_sae"]))
     assert seen["hook_sae_out"][0] == torch.bfloat16
     assert out_hooked[0].dtype == torch.bfloat16 and out_sparse[0].dtype == torch.bfloat16
-    # the hooked route rounds sae_in / hidden_pre / feature_acts / sae_out to bf16 on the way (as the reference does): two bf16 ulps
-    assert rel_err(out_hooked[0].float(), out_sparse[0].float()) <= 2e-2
-    assert abs(out_hooked[3].item() - out_sparse[3].item()) <= 2e-2 * abs(out_sparse[3].item())
+    # the hooked route rounds hidden_pre to bf16 before TopK (as the reference does): bf16 ties change the support on some rows, which
+    # is what puts the reference's own bf16 output 8e-2 from its fp32 output on this fixture -- same order of magnitude expected here
+    assert rel_err(out_hooked[0].float(), out_sparse[0].float()) <= 1e-1
+    assert abs(out_hooked[3].item() - out_sparse[3].item()) <= 5e-2 * abs(out_sparse[3].item())
     sae_in, feats = sae.encode(x)
     assert sae_in.dtype == torch.bfloat16 and feats.dtype == torch.bfloat16 and feats.shape == (gold["batch"], gold["d_sae"])
     assert int((feats > 0).sum(dim=1).max()) <= gold["k"]

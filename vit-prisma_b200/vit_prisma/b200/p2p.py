@@ -280,9 +280,11 @@ class SaeDPEngine(SaeStepEngine):
         self.gb_enc_red, self.gb_dec_red, self.fired_red = torch.zeros(F, device=dev), torch.zeros(d, device=dev), torch.zeros(F, device=dev)
         self.part_accum = torch.zeros(4, device=dev)        # gradient-norm partial + encoder row-norm maxima of the owned slice
         import os
-        # the W_dec half of the all-gather runs on a side stream under the next step's prep / encoder GEMM / select (it is first
-        # read by the next decode); PRISMA_P2P_OVERLAP=0 keeps the whole all-gather inside the Adam kernel
-        self.overlap_dec = os.environ.get("PRISMA_P2P_OVERLAP", "1") != "0" and g.world > 1
+        # PRISMA_P2P_OVERLAP=1: the W_dec half of the all-gather runs on a side stream under the next step's prep / encoder GEMM /
+        # select (it is first read by the next decode).  OFF by default: measured no gain at 8 ranks and a loss at 2 (run 17's trace:
+        # the SM-driven push kernel slows the concurrent candidate GEMM by as much as the Adam kernel gets shorter); a copy-engine
+        # push would not share SMs with the GEMM -- not built.
+        self.overlap_dec = os.environ.get("PRISMA_P2P_OVERLAP", "0") == "1" and g.world > 1
         self._side = torch.cuda.Stream(device=dev) if self.overlap_dec else None
         self._trace = [] if os.environ.get("PRISMA_P2P_TRACE", "0") == "1" else None      # per-step CUDA-event marks (trace_report)
         self._trace_step = []
