@@ -7,8 +7,9 @@ bf16 initial state: the reference in bf16 and the reference in fp32.  Bars:
   * step-0 reconstruction on identical bf16 weights: one bf16 rounding from the reference's fp32 output; its bf16 output is itself
     8e-2 from that (bf16 ties change the TopK support), so against it the bar is the triangle inequality, not 1e-2;
   * losses: within 1e-2 of the reference's bf16 run, within 1e-4 of its fp32 run (our arithmetic is the fp32 one);
-  * parameters after every step: bf16 tensors, no further from the fp32 trajectory than one bf16 rounding (2^-8 relative), and never
-    further from it than the reference's own bf16 run is.
+  * parameters after every step: bf16 tensors, no further from the fp32 trajectory than one bf16 rounding (2^-8 relative); the two
+    matrices never further from it than the reference's own bf16 run is (the biases are printed, not asserted: a parameter the
+    reference's bf16 Adam happens not to move at all can sit closer to the fp32 run than one rounding).
 """
 import contextlib
 import io
@@ -82,8 +83,11 @@ def test_bf16_sae_trains_on_fp32_masters_and_exports_bf16_parameters():
             scale = float(ref32.abs().max())
             ours = float((mine.float().cpu() - ref32).abs().max())
             theirs = float((ref16 - ref32).abs().max())
+            # one bf16 rounding of the fp32 trajectory: |x - bf16(x)| <= 2^-8 |x| (half a spacing relative to the bottom of a binade)
             assert ours <= 2.0 ** -8 * scale + 1e-7, f"step {s} {name}: {ours:.3e} from the fp32 trajectory (one bf16 rounding = {2.0 ** -8 * scale:.3e})"
-            assert ours <= theirs + 2.0 ** -9 * scale + 1e-7, f"step {s} {name}: further from the fp32 trajectory ({ours:.3e}) than the reference's bf16 run ({theirs:.3e})"
+            print(f"step {s} {name}: ours {ours:.2e} / reference-bf16 {theirs:.2e} from the fp32 trajectory (scale {scale:.2e})")
+            if name in ("W_dec", "W_enc"):     # the matrices: the reference's bf16 Adam drifts by several roundings (2e-3 .. 6e-3 on W_dec, generator log)
+                assert ours <= theirs + 2.0 ** -9 * scale + 1e-7, f"step {s} {name}: further from the fp32 trajectory ({ours:.3e}) than the reference's bf16 run ({theirs:.3e})"
     # the masters follow a load_state_dict (version check), and the module forward sees the trained parameters
     eng = sae.step_engine()
     assert eng.W_dec.dtype == torch.float32 and eng.m_dec.dtype == torch.float32
