@@ -19,7 +19,7 @@ def _run(*args, env=None):
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, capture_output=True, text=True, timeout=900, env=e)
 
 
-@pytest.mark.parametrize("workload", ["vit", "sae"])
+@pytest.mark.parametrize("workload", ["vit", "sae", "cfg5", "sae_fwd"])
 def test_reference_arm_prints_one_json_line(workload):
     out = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--workload", workload)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -32,7 +32,7 @@ def test_reference_arm_prints_one_json_line(workload):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
-    assert (d["unit"], d["config"]["workload"][:3]) == (("tokens/s", "sae") if workload == "sae" else ("images/s", "vit"))
+    assert (d["unit"], d["config"]["workload"][:3]) == (("images/s", "vit") if workload == "vit" else ("tokens/s", "sae"))
 
 
 def test_reference_arm_nonzero_ranks_exit_quietly():

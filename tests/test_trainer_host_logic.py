@@ -51,3 +51,27 @@ def test_step_engine_rejects_unbuilt_training_activations():
     sae = StandardSparseAutoencoder(_cfg(activation_fn_str="relu", activation_fn_kwargs={}, lp_norm=2))
     with pytest.raises(NotImplementedError, match="lp_norm"):
         sae.step_engine()
+
+
+def test_bf16_module_keeps_reference_storage_and_refuses_cpu_compute(tmp_path):
+    """cfg #5 class: `_dtype="bfloat16"` (the reference's dtype table has no such entry) gives bf16 parameters / state dict with the
+    reference's names and shapes; the fp32 masters the step engine trains do not exist until a CUDA engine is bound; on a host-
+    resident module every compute entry (forward, step_engine) fails loudly instead of computing on the CPU."""
+    cfg = _cfg(_dtype="bfloat16")
+    assert cfg.dtype == torch.bfloat16
+    sae = StandardSparseAutoencoder(cfg)
+    assert sae.low_precision and sae._masters is None
+    sd = sae.state_dict()
+    assert {k: (tuple(v.shape), v.dtype) for k, v in sd.items()} == {
+        "W_dec": ((32, 16), torch.bfloat16), "W_enc": ((16, 32), torch.bfloat16), "b_enc": ((32,), torch.bfloat16), "b_dec": ((16,), torch.bfloat16)}
+    assert sae.W_enc.data.t().is_contiguous()
+    sae.export_masters()                                           # nothing to export yet: a no-op, not an error
+    with pytest.raises(PrismaB200Error, match="no CPU fallback"):
+        sae(torch.randn(4, 16, dtype=torch.bfloat16))
+    with pytest.raises(PrismaB200Error, match="no CPU fallback"):
+        sae.step_engine()
+    # config round trip keeps the dtype string; fp32 modules are not "low precision"
+    path = tmp_path / "config.json"
+    cfg.save_config(str(path))
+    assert VisionModelSAERunnerConfig.load_config(str(path)).dtype == torch.bfloat16
+    assert not StandardSparseAutoencoder(_cfg()).low_precision
