@@ -14,8 +14,10 @@ checked against an independent derivation that is itself pinned to the reference
   set_decoder_norm_to_unit_norm / remove_gradient_...   sae/sae.py:275-297
   VisionSAETrainer.train_step ordering, clipping, Adam  sae/train_sae.py:278-411 (torch.optim.Adam defaults)
   cosineannealingwarmup schedule                        sae/training/get_scheduler.py:42-53, train_sae.py:235
+  GatedSparseAutoencoder forward / training step        sae/sae.py:648-792
+  Transcoder forward / training step on (input, target) sae/transcoder.py:6-116, train_sae.py:299-301
 
-Pinning: tests/test_oracle_golden.py compares against tests/golden/sae_tiny_*.pt, produced by running the
+Pinning: tests/test_oracle_golden.py compares against tests/golden/{sae_tiny_*, sae_gated_*, transcoder_*, sae_bf16_v}.pt, produced by running the
 UNMODIFIED reference modules + torch autograd + torch.optim.Adam in the build container
 (tests/golden/make_golden_sae.py).  The reference has no numeric test of this path, so the
 reference itself, run here, is the anchor.
@@ -228,3 +230,74 @@ def gated_train_step(p: Dict[str, torch.Tensor], state, x: torch.Tensor, lr: flo
         p[name] -= (lr / (1 - b1 ** t)) * st["m"] / (st["v"].sqrt() / math.sqrt(1 - b2 ** t) + eps)
     out.update(raw_grads=raw, grad_norm=total_norm, clip=clip, l0=(acts > 0).float().sum(-1).mean())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ Transcoder (sae/transcoder.py:6-116)
+def transcoder_forward_grads(p: Dict[str, torch.Tensor], x: torch.Tensor, y: torch.Tensor, mode: str, act: str, k: int, l1_coefficient: float):
+    """Forward, loss and closed-form gradients of the reference Transcoder: the encoder reads the INPUT activation ``x``
+    (normalised, minus ``b_dec``), the decoder reconstructs the TARGET activation ``y`` with its own bias ``b_dec_out`` and an
+    optional linear skip ``x @ W_skip^T`` (added before the output de-normalisation, which uses the INPUT's row mean / std,
+    transcoder.py:75-78); the loss is ``_compute_mse_loss(y, out)`` (sae.py:144-149) plus the L1 term for dense activations.
+    p: W_enc [d,F], W_dec [F,d_out], b_enc [F], b_dec [d], b_dec_out [d_out], optional W_skip [d_out, d]."""
+    Bt, d_out = y.shape
+    xn, mu, std = normalise_in(x, mode)
+    sae_in = xn - p["b_dec"]                                            # transcoder.py:33-37
+    hidden_pre = sae_in @ p["W_enc"] + p["b_enc"]                      # :39-46
+    if act == "topk":
+        top = torch.topk(hidden_pre, k=k, dim=-1)
+        acts = torch.zeros_like(hidden_pre).scatter_(-1, top.indices, torch.relu(top.values))
+    else:
+        acts = torch.relu(hidden_pre)
+    out_n = acts @ p["W_dec"] + p["b_dec_out"]                         # :56-64
+    if "W_skip" in p:
+        out_n = out_n + x @ p["W_skip"].t()                             # :75-76 (the raw input, not the normalised one)
+    out = out_n * std + mu if mode == "layer_norm" else (out_n * std if mode == "constant_norm_rescale" else out_n)   # :78
+    nf = torch.norm(y - y.mean(dim=0, keepdim=True), p=2, dim=-1, keepdim=True)
+    mse = (((out - y) ** 2) / nf).sum() / (Bt * d_out)                 # :80
+    l1 = None if act == "topk" else l1_coefficient * acts.abs().sum(dim=1).sum() / Bt   # :89-97
+    loss = mse + (l1 if l1 is not None else 0.0)
+    scale = std if mode != "none" else torch.ones_like(nf)
+    g = 2.0 * (out - y) * scale / (nf * Bt * d_out)                    # dL/d out_n
+    grads = {"W_dec": acts.t() @ g, "b_dec_out": g.sum(0)}
+    if "W_skip" in p:
+        grads["W_skip"] = g.t() @ x
+    d_acts = g @ p["W_dec"].t()
+    if l1 is not None:
+        d_acts = d_acts + l1_coefficient / Bt
+    d_pre = d_acts * (acts > 0)
+    grads["W_enc"] = sae_in.t() @ d_pre
+    grads["b_enc"] = d_pre.sum(0)
+    grads["b_dec"] = -(d_pre @ p["W_enc"].t()).sum(0)                   # b_dec only enters through sae_in = xn - b_dec
+    return dict(sae_out=out, feature_acts=acts, loss=loss, mse=mse, l1=l1, grads=grads)
+
+
+def transcoder_train_step(p: Dict[str, torch.Tensor], state, x: torch.Tensor, y: torch.Tensor, lr: float, t: int, mode: str, act: str, k: int,
+                          l1_coefficient: float, max_grad_norm: Optional[float] = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                          since_fired: Optional[torch.Tensor] = None, act_freq: Optional[torch.Tensor] = None):
+    """One reference train_step on an (input, target) pair (train_sae.py:299-301, 335-344, 392-401), in place on p / state."""
+    p["W_dec"] /= torch.norm(p["W_dec"], dim=1, keepdim=True)           # :306-307
+    out = transcoder_forward_grads(p, x, y, mode, act, k, l1_coefficient)
+    grads = out["grads"]
+    raw = {n: g.clone() for n, g in grads.items()}
+    acts = out["feature_acts"]
+    if since_fired is not None:
+        did_fire = (acts > 0).float().sum(-2) > 0
+        since_fired += 1
+        since_fired[did_fire] = 0
+    if act_freq is not None:
+        act_freq += (acts.abs() > 0).float().sum(0)
+    total_norm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+    if max_grad_norm:
+        clip = min(1.0, max_grad_norm / (total_norm.item() + 1e-6))
+        for g in grads.values():
+            g *= clip
+    par = (grads["W_dec"] * p["W_dec"]).sum(1, keepdim=True)
+    grads["W_dec"] = grads["W_dec"] - par * p["W_dec"]
+    b1, b2 = betas
+    for name in p:
+        st, g = state[name], grads[name]
+        st["m"].mul_(b1).add_(g, alpha=1 - b1)
+        st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+        p[name] -= (lr / (1 - b1 ** t)) * st["m"] / (st["v"].sqrt() / math.sqrt(1 - b2 ** t) + eps)
+    return dict(loss=out["loss"], mse=out["mse"], l1=out["l1"], l0=(acts > 0).float().sum(-1).mean(), grad_norm=total_norm,
+                sae_out=out["sae_out"], feature_acts=acts, raw_grads=raw)

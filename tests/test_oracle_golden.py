@@ -179,3 +179,44 @@ def test_sae_oracle_follows_the_fp32_twin_of_the_bf16_fixture():
             assert_close(p[n], rec32["params_after"][n], 2e-5, f"step {s} param {n}")
         assert abs(rec16["mse"] - rec32["mse"]) <= 1e-2 * rec32["mse"]
         assert rec16["params_after"]["W_dec"].dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("tag", ["t", "u"])
+def test_transcoder_oracle_matches_reference_training(tag):
+    """transcoder_{t,u}.pt: the unmodified reference Transcoder (t: ReLU + L1, layer_norm, skip matrix; u: TopK, no normalisation, no skip)
+    driven by autograd + torch.optim.Adam for 5 steps on (input, target) pairs -- forward, loss terms, all gradients (closed form
+    here), clipping, decoder projection, Adam and the schedule."""
+    from oracle.sae_oracle import transcoder_train_step
+    gold = load_golden(f"transcoder_{tag}.pt")
+    g = torch.Generator().manual_seed(gold["data_seed"])
+    n, d = gold["batch"] * gold["n_steps"], gold["d"]
+    x_all = torch.randn(n, d, generator=g) * 2.0 + torch.randn(d, generator=g)
+    M = torch.randn(d, d, generator=g) / d ** 0.5
+    y_all = torch.tanh(x_all @ M) * 1.5 + 0.3 * torch.randn(n, d, generator=g) + torch.randn(d, generator=g)
+    p = {k: v.clone() for k, v in gold["init"].items()}
+    assert ("W_skip" in p) == gold["skip"]
+    state = new_adam_state(p)
+    since_fired, act_freq = torch.zeros(gold["d_sae"]), torch.zeros(gold["d_sae"])
+    B = gold["batch"]
+    for s, rec in enumerate(gold["steps"]):
+        lr = gold["lr"] * lr_multiplier(s, gold["warm_up_steps"], gold["total_steps"], gold["lr_end"])
+        assert abs(lr - rec["lr"]) < 1e-12
+        out = transcoder_train_step(p, state, x_all[s * B:(s + 1) * B], y_all[s * B:(s + 1) * B], lr, s + 1, gold["norm"], gold["act"], gold["k"],
+                                    gold["l1_coefficient"], since_fired=since_fired, act_freq=act_freq)
+        assert abs(out["loss"].item() - rec["loss"]) <= 1e-5 * abs(rec["loss"])
+        assert abs(out["mse"].item() - rec["mse"]) <= 1e-5 * abs(rec["mse"])
+        assert (out["l1"] is None) == (rec["l1"] is None)
+        if rec["l1"] is not None:
+            assert abs(out["l1"].item() - rec["l1"]) <= 1e-5 * abs(rec["l1"])
+        assert abs(out["l0"].item() - rec["l0"]) < 1e-5
+        assert abs(out["grad_norm"].item() - rec["grad_norm"]) <= 1e-4 * rec["grad_norm"]
+        assert_close(out["sae_out"], rec["sae_out"], 1e-5, f"step {s} sae_out")
+        if "feature_acts" in rec:
+            assert_close(out["feature_acts"], rec["feature_acts"], 1e-5, "feature_acts")
+        if "raw_grads" in rec:
+            for name in p:
+                assert_close(out["raw_grads"][name], rec["raw_grads"][name], 2e-5, f"step {s} grad {name}")
+        if "params_after" in rec:
+            for name in p:
+                assert_close(p[name], rec["params_after"][name], 2e-5, f"step {s} param {name}")
+    assert torch.equal(since_fired, gold["since_fired"]) and torch.equal(act_freq, gold["act_freq"])
