@@ -207,3 +207,18 @@ def test_product_synthetic_recipe_equals_the_oracle_recipe():
     shapes = vit_oracle.state_dict_shapes(tiny)
     a, b = synthetic.recipe_state_dict(shapes, 99), vit_oracle.recipe_state_dict(shapes, 99)
     assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_c_abi_header_is_plain_c(tmp_path):
+    """include/prisma_b200.h is the drop-in boundary: it must compile as C99 (and as C++) with nothing but the standard headers --
+    no torch, no CUDA headers, no C++-only constructs."""
+    import shutil
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "prisma_b200.h"\nint main(void) { return (int)sizeof(PbGemm) == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cc, flags in (("gcc", ["-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror"]), ("g++", ["-x", "c++", "-std=c++11", "-Wall", "-Werror"])):
+        if shutil.which(cc) is None:
+            pytest.skip(f"{cc} not available")
+        out = subprocess.run([cc, *flags, "-fsyntax-only", f"-I{inc}", str(src)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
