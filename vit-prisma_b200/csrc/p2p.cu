@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) k_p2p_sum_small3(P2PTables t, float* __re
 
 // ------------------------------------------------------------------------------------------- reduce-scatter + norm
 // rows [f0, f1) of both gradient matrices: own += sum of peers; partial ||g||^2 -> every peer's norm_parts[rank]
-// One gradient array's owned slice: own[i] = sum over ranks (rank order) of that rank's copy; returns this thread's share of ||.||^2.
+// One gradient array's owned slice: own[i] = sum over ranks of that rank's copy, owner first then (rank + j) % world -- a fixed order per row; returns this thread's share of ||.||^2.
 // W = compile-time rank count (ranks >= t.world are skipped when W is the generic PB_MAX_RANKS), U = elements per trip.
 template <int W, int U>
 __device__ __forceinline__ float rs_peer_slice(const P2PTables& t, int m, int64_t base4, int64_t n4, float4* __restrict__ own, int64_t tid,
